@@ -1,0 +1,202 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on seeded inputs.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+The reference modules ``mot_neural_solver.models.mpn`` and ``mot_neural_solver.utils.graph``
+are imported from /root/reference/src with the pure-torch ``torch_scatter`` stand-in of
+``tests/golden/torch_scatter_stub`` (the only import they miss in this image).  Inputs and
+weights come from ``mpntrackseg_b200.synth`` (seeded), so the fixtures hold outputs only,
+plus an input checksum that the tests re-verify.  ``data/mot_graph.py`` and
+``tracker/mpn_tracker.py`` cannot be imported here (torch_geometric / pycocotools are
+absent); their <=35 lines of glue around the imported functions are applied inline below,
+line-cited.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, 'torch_scatter_stub'))
+sys.path.insert(0, '/root/reference/src')
+
+import pandas as pd  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+from mot_neural_solver.models.mpn import MOTMPNet as RefMOTMPNet  # noqa: E402
+from mot_neural_solver.utils.graph import (  # noqa: E402
+    compute_edge_feats_dict, get_knn_mask, get_time_valid_conn_ixs)
+
+from mpntrackseg_b200 import synth  # noqa: E402
+from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params  # noqa: E402
+
+from cases import CASES, TRACKER_CASE, checksum  # noqa: E402
+
+
+def det_df(win):
+    return pd.DataFrame(synth.det_columns(win))
+
+
+def ref_build_graph(win, ds, inference_mode, max_frame_dist):
+    """Inline of MOTGraph._get_edge_ixs + construct_graph_object around the imported
+    reference functions (reference: data/mot_graph.py:206-219, 292-312)."""
+    df = det_df(win)
+    edge_ixs = get_time_valid_conn_ixs(frame_num=win.frame, max_frame_dist=max_frame_dist,
+                                       use_cuda=False)
+    n_cand = edge_ixs.shape[1]
+    if not inference_mode and ds['top_k_nns'] is not None:
+        d = F.pairwise_distance(win.reid[edge_ixs[0]], win.reid[edge_ixs[1]])
+        keep = get_knn_mask(pwise_dist=d, edge_ixs=edge_ixs, num_nodes=win.N,
+                            top_k_nns=ds['top_k_nns'], reciprocal_k_nns=ds['reciprocal_k_nns'],
+                            symmetric_edges=False, use_cuda=False)
+        edge_ixs = edge_ixs.T[keep].T
+    fd = compute_edge_feats_dict(edge_ixs=edge_ixs, det_df=df, fps=win.fps, use_cuda=False)
+    feats = torch.stack([fd[n] for n in ds['edge_feats_to_use'] if n in fd]).T
+    emb = []
+    for i in range(0, edge_ixs[0].shape[0], 50000):
+        emb.append(F.pairwise_distance(win.reid[edge_ixs[0][i:i + 50000]],
+                                       win.reid[edge_ixs[1][i:i + 50000]]).view(-1, 1))
+    emb = torch.cat(emb, dim=0)
+    if 'emb_dist' in ds['edge_feats_to_use']:
+        feats = torch.cat((feats, emb), dim=1)
+    edge_attr = torch.cat((feats, feats), dim=0)
+    edge_index = torch.cat((edge_ixs, torch.stack((edge_ixs[1], edge_ixs[0]))), dim=1)
+    dists = torch.cat((emb, emb)).view(-1) if inference_mode else None
+    return n_cand, edge_index, edge_attr, dists
+
+
+def centred_params(mp, wseed, gain, ref_model, data):
+    """Weights from synth.make_params, classifier bias shifted so that the last step's
+    logits have median 0 (default-init logits never cross 0)."""
+    P = synth.make_params(mp, seed=wseed, gain=gain)
+    ref_model.load_state_dict(P, strict=True)
+    with torch.no_grad():
+        last = core_forward(ref_model, data)['classified_edges'][-1]
+    shift = float(last.median())
+    key = [k for k in P if k.startswith('classifier.edge_model') and k.endswith('bias')][-1]
+    P[key] = P[key] - shift
+    ref_model.load_state_dict(P, strict=True)
+    return P, shift
+
+
+def core_forward(model, data):
+    """The reference forward restricted to the modules the edge logits depend on: the
+    same sub-module calls, in the same order, as MOTMPNet.forward
+    (reference: models/mpn.py:351-381 minus the x_ext / mask lines 356,373,377(ext),384-385)."""
+    x = model.global_avgpool(data.x).view(data.x.size(0), -1)
+    e_lat, x_lat = model.encoder(data.edge_attr, x)
+    e0, x0 = e_lat, x_lat
+    first = model.num_enc_steps - model.num_class_steps + 1
+    out = {'classified_edges': []}
+    for step in range(1, model.num_enc_steps + 1):
+        e_lat = torch.cat((e0, e_lat), dim=1)
+        x_lat = torch.cat((x0, x_lat), dim=1)
+        x_lat, e_lat = model.MPNet(x_lat, data.edge_index, e_lat)
+        dec, _ = model.classifier(e_lat)
+        if step >= first:
+            out['classified_edges'].append(dec)
+    if model.num_enc_steps == 0:
+        dec, _ = model.classifier(e_lat)
+        out['classified_edges'].append(dec)
+    out['node_state'], out['edge_state'] = x_lat, e_lat
+    return out
+
+
+class Data:
+    pass
+
+
+def run_case(name, c):
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    mp = default_graph_model_params(*c['steps'])
+    mfd = c.get('max_frame_dist', 'max')
+    n_cand, edge_index, edge_attr, _ = ref_build_graph(win, ds, False, mfd)
+    data = Data()
+    data.x, data.edge_index, data.edge_attr = win.x, edge_index, edge_attr
+    data.x_ext = win.x_ext
+    torch.manual_seed(0)
+    model = RefMOTMPNet(mp).eval()
+    P, shift = centred_params(mp, c['wseed'], c['gain'], model, data)
+    with torch.no_grad():
+        core = core_forward(model, data)
+        logits = torch.stack([t.view(-1) for t in core['classified_edges']])
+        out = dict(
+            n_candidates=np.int64(n_cand),
+            edge_index=edge_index.numpy().astype(np.int32),
+            edge_attr=edge_attr.numpy(),
+            logits=logits.numpy(),
+            node_state=core['node_state'].numpy(), edge_state=core['edge_state'].numpy(),
+            bias_shift=np.float64(shift),
+            input_checksum=checksum(win.frame, win.reid, win.x, win.bb_height, win.feet_x),
+            param_checksum=checksum(*P.values()))
+        if c.get('full'):
+            full = model(data)                                   # the reference's own forward
+            fl = torch.stack([t.view(-1) for t in full['classified_edges']])
+            assert torch.equal(fl, logits), 'core sub-module loop != MOTMPNet.forward logits'
+            m = full['mask_predictions'][-1]
+            out['mask_last_sample'] = m[:, 0, ::7, ::7].numpy()
+            out['mask_step_means'] = np.array([float(t.double().mean()) for t in full['mask_predictions']])
+    stats = dict(N=win.N, E=edge_index.shape[1], cand=n_cand,
+                 logit_std=float(logits[-1].std()) if logits.numel() else 0.0,
+                 frac_pos=float((logits[-1] > 0).float().mean()) if logits.numel() else 0.0)
+    print(name, stats)
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+
+
+def run_tracker_case():
+    """Whole-sequence graph without KNN, then one sliding window pruned and evaluated the
+    way MPNTracker does (reference: tracker/mpn_tracker.py:80-84,167-179,107-135)."""
+    c = TRACKER_CASE
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    mp = default_graph_model_params(*c['steps'])
+    fpg = ds['frames_per_graph']
+    max_frame_dist = 1 * (fpg - 1)                                       # mpn_tracker.py:80-81
+    n_cand, edge_index, edge_attr, dists = ref_build_graph(win, ds, True, max_frame_dist)
+    frames = torch.unique(win.frame)
+    start, end = int(frames[2]), int(frames[2 + fpg - 1])
+    nodes_mask = (start <= win.frame) & (win.frame <= end)               # mpn_tracker.py:171
+    edges_mask = nodes_mask[edge_index[0]] & nodes_mask[edge_index[1]]   # mpn_tracker.py:172-173
+    first = int(torch.nonzero(nodes_mask)[0])
+    sub_ei = edge_index.T[edges_mask].T - first                          # mpn_tracker.py:179
+    sub_attr, sub_d = edge_attr[edges_mask], dists[edges_mask]
+    n_sub = int(nodes_mask.sum())
+    keep = get_knn_mask(pwise_dist=sub_d, edge_ixs=sub_ei, num_nodes=n_sub, top_k_nns=ds['top_k_nns'],
+                        use_cuda=False, reciprocal_k_nns=ds['reciprocal_k_nns'], symmetric_edges=True)
+    data = Data()
+    data.x, data.x_ext = win.x[nodes_mask], None
+    data.edge_index, data.edge_attr = sub_ei.T[keep].T, sub_attr[keep]
+    model = RefMOTMPNet(mp).eval()
+    P, shift = centred_params(mp, c['wseed'], c['gain'], model, data)
+    with torch.no_grad():
+        core = core_forward(model, data)
+    pruned = torch.sigmoid(core['classified_edges'][-1].view(-1))        # mpn_tracker.py:129
+    preds = torch.zeros(keep.shape[0])
+    preds[keep] = pruned                                                 # mpn_tracker.py:133-134
+    print('tracker_window', dict(N=win.N, E_full=edge_index.shape[1], n_sub=n_sub,
+                                 E_sub=int(edges_mask.sum()), kept=int(keep.sum()),
+                                 logit_std=float(core['classified_edges'][-1].std())))
+    np.savez_compressed(
+        os.path.join(HERE, 'tracker_window.npz'),
+        n_candidates=np.int64(n_cand), full_edge_index=edge_index.numpy().astype(np.int32),
+        full_edge_attr=edge_attr.numpy(), full_dists=dists.numpy(),
+        window=np.array([start, end]), keep=keep.numpy(), edge_preds=preds.numpy(),
+        bias_shift=np.float64(shift),
+        input_checksum=checksum(win.frame, win.reid, win.x, win.bb_height, win.feet_x),
+        param_checksum=checksum(*P.values()))
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(os.cpu_count() or 1)
+    only = sys.argv[1:]
+    for name, case in CASES.items():
+        if not only or name in only:
+            run_case(name, case)
+    if not only or 'tracker_window' in only:
+        run_tracker_case()

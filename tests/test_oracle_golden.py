@@ -1,0 +1,120 @@
+"""Pins the CPU oracle (oracle/) against outputs of the unmodified reference
+(tests/golden/*.npz, written by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, load_case
+from mpntrackseg_b200 import synth
+from oracle import graph_ref, mpn_ref
+
+GRAPH_CASES = list(CASES)
+
+
+@pytest.mark.parametrize('name', GRAPH_CASES)
+def test_graph_build_matches_reference(name):
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, c['ds'],
+                              inference_mode=False, max_frame_dist=c['max_frame_dist'])
+    pairs = graph_ref.time_valid_pairs(win.frame, c['max_frame_dist'])
+    assert pairs.shape[1] == int(gold['n_candidates'])
+    assert np.array_equal(g['edge_index'].numpy(), gold['edge_index'].astype(np.int64))
+    # same torch ops on the same CPU: bit-exact features
+    assert np.array_equal(g['edge_attr'].numpy(), gold['edge_attr'])
+
+
+@pytest.mark.parametrize('name', GRAPH_CASES)
+def test_core_forward_matches_reference(name):
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    with torch.no_grad():
+        out = mpn_ref.mpn_forward(c['P'], c['mp'], win.x, ei, ea, return_state=True)
+    logits = torch.stack([t.view(-1) for t in out['classified_edges']]).numpy()
+    assert logits.shape == gold['logits'].shape
+    # identical op sequence -> expect (near) bit equality; allow 1e-5 for BLAS blocking
+    np.testing.assert_allclose(logits, gold['logits'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out['edge_state'].numpy(), gold['edge_state'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out['node_state'].numpy(), gold['node_state'], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', ['tiny_full'])
+def test_full_forward_with_mask_branch(name):
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    with torch.no_grad():
+        out = mpn_ref.mpn_forward(c['P'], c['mp'], win.x, ei, ea, x_ext=win.x_ext)
+    logits = torch.stack([t.view(-1) for t in out['classified_edges']]).numpy()
+    np.testing.assert_allclose(logits, gold['logits'], rtol=1e-5, atol=1e-5)
+    assert len(out['mask_predictions']) == c['mp']['num_class_steps']
+    m = out['mask_predictions'][-1]
+    assert tuple(m.shape) == (win.N, 1, 56, 56)
+    np.testing.assert_allclose(m[:, 0, ::7, ::7].numpy(), gold['mask_last_sample'], rtol=1e-4, atol=1e-4)
+    means = np.array([float(t.double().mean()) for t in out['mask_predictions']])
+    np.testing.assert_allclose(means, gold['mask_step_means'], rtol=1e-4, atol=1e-5)
+
+
+def test_tracker_window_glue():
+    c = load_case('tracker_window')
+    win, gold, ds = c['win'], c['gold'], c['ds']
+    fpg = ds['frames_per_graph']
+    g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds,
+                              inference_mode=True, max_frame_dist=fpg - 1)
+    assert np.array_equal(g['edge_index'].numpy(), gold['full_edge_index'].astype(np.int64))
+    assert np.array_equal(g['edge_attr'].numpy(), gold['full_edge_attr'])
+    assert np.array_equal(g['reid_emb_dists'].numpy(), gold['full_dists'])
+    start, end = (int(v) for v in gold['window'])
+    nodes = (win.frame >= start) & (win.frame <= end)
+    edges = nodes[g['edge_index'][0]] & nodes[g['edge_index'][1]]
+    first = int(torch.nonzero(nodes)[0])
+    sub_ei = g['edge_index'][:, edges] - first
+    ei, ea, keep = graph_ref.prune_window(sub_ei, g['edge_attr'][edges], g['reid_emb_dists'][edges],
+                                          int(nodes.sum()), ds)
+    assert np.array_equal(keep.numpy(), gold['keep'])
+    with torch.no_grad():
+        out = mpn_ref.mpn_forward(c['P'], c['mp'], win.x[nodes], ei, ea)
+    preds = mpn_ref.window_edge_preds(out['classified_edges'], keep)
+    np.testing.assert_allclose(preds.numpy(), gold['edge_preds'], rtol=1e-5, atol=1e-6)
+
+
+def test_knn_mask_independent_restatement():
+    """The dense-argsort restatement agrees with a per-node sort formulation."""
+    win = synth.make_window(T=7, D=9, k=8, seed=5)
+    pairs = graph_ref.time_valid_pairs(win.frame)
+    d = graph_ref.pair_reid_dist(win.reid, pairs)
+    for recip in (True, False):
+        got = graph_ref.knn_keep_mask(d, pairs, win.N, 8, recip, symmetric_edges=False)
+        nbr = [[] for _ in range(win.N)]
+        for e in range(pairs.shape[1]):
+            i, j = int(pairs[0, e]), int(pairs[1, e])
+            nbr[i].append((float(d[e]), j))
+            nbr[j].append((float(d[e]), i))
+        top = [set(j for _, j in sorted(l)[:8]) for l in nbr]
+        exp = []
+        for e in range(pairs.shape[1]):
+            i, j = int(pairs[0, e]), int(pairs[1, e])
+            a, b = j in top[i], i in top[j]
+            exp.append((a and b) if recip else (a or b))
+        assert got.tolist() == exp
+
+
+def test_segment_softmax_sums_to_one_and_handles_gaps():
+    src = torch.tensor([[0.3], [2.0], [-1.0], [5.0]])
+    idx = torch.tensor([0, 0, 3, 3])
+    w = mpn_ref.segment_softmax(src, idx)
+    s = mpn_ref.segment_add(w, idx, 4).view(-1)
+    assert torch.allclose(s, torch.tensor([1.0, 0.0, 0.0, 1.0]), atol=1e-6)
+
+
+def test_loss_zero_positives_and_weighting():
+    logits = [torch.tensor([[0.2], [-0.4], [1.5]])]
+    assert float(mpn_ref.weighted_bce_loss(logits, torch.zeros(3))) > 0
+    lab = torch.tensor([1.0, 0.0, 0.0])
+    l = mpn_ref.weighted_bce_loss(logits, lab)
+    x = logits[0].view(-1)
+    manual = (2.0 * lab * torch.nn.functional.softplus(-x) + (1 - lab) * torch.nn.functional.softplus(x)).mean()
+    assert torch.allclose(l, manual, atol=1e-6)
