@@ -1,0 +1,196 @@
+/*
+ * mpntrack_b200.h -- C ABI of libmpntrack_b200.so (sm_100a CUDA kernels for the
+ * MPNTrackSeg neural-message-passing hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - tensors are dense row-major; float = fp32, indices as stated (the reference uses
+ *     int64 edge_index, the library converts to int32 internally);
+ *   - every function returns 0 on success, a negative MPN_E* code otherwise;
+ *     mpn_last_error() returns a human-readable message for the calling thread;
+ *   - functions are re-entrant and only enqueue work on `stream`, except the ones
+ *     documented as "syncs", which must read a device counter to size their output
+ *     (the same place where the reference's torch.where / boolean indexing syncs).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference's src/mot_neural_solver/).
+ */
+#ifndef MPNTRACK_B200_H
+#define MPNTRACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPN_OK 0
+#define MPN_EINVAL (-1)   /* bad argument (shape, null pointer, unsupported width) */
+#define MPN_ECUDA (-2)    /* CUDA runtime error, see mpn_last_error() */
+#define MPN_ENOSPC (-3)   /* caller-provided output capacity too small */
+
+const char* mpn_last_error(void);
+/* ABI version of the shared object; bumped on any signature change. */
+int mpn_abi_version(void);
+/* Compute capability major*10+minor of the current device (100 on B200), <0 on error. */
+int mpn_device_arch(void);
+
+/* Number of kernel launches this library has issued so far in this process (monotonic). */
+long long mpn_launch_count(void);
+/* Per-kernel device timing of the message-passing kernels: between _begin and _end every
+ * mp_edge_kernel / mp_node_kernel launch is bracketed by CUDA events on its own stream.
+ * _end synchronises the device and returns summed milliseconds and launch counts,
+ * index 0 = edge kernel, 1 = node kernel. */
+int mpn_profile_begin(void);
+int mpn_profile_end(double* h_ms /*[2]*/, long long* h_launches /*[2]*/);
+
+/* ------------------------------------------------------------------ graph construction */
+
+/* utils/graph.py:6-37  get_time_valid_conn_ixs(frame_num, max_frame_dist, ..)
+ * Pairs (i<j) with 0 < |frame_i - frame_j| <= max_frame_dist (max_frame_dist < 0 means
+ * 'max': no upper bound), restricted to nodes of the same window: node_graph_ptr[G+1]
+ * gives each window's node range (pass NULL, G=0 for a single window).  Output order:
+ * ascending i then ascending j.  Two-phase: _count writes per-row counts and the
+ * exclusive scan row_start[N+1] (row_start[N] = total); SYNCS to return *h_total.
+ * _fill writes pairs at row_start offsets. */
+int mpn_time_valid_pairs_count(const int64_t* frame_num, int64_t num_nodes,
+                               const int64_t* node_graph_ptr, int64_t num_graphs,
+                               int64_t max_frame_dist, int64_t* row_start /*[N+1]*/,
+                               int64_t* h_total, void* stream);
+int mpn_time_valid_pairs_fill(const int64_t* frame_num, int64_t num_nodes,
+                              const int64_t* node_graph_ptr, int64_t num_graphs,
+                              int64_t max_frame_dist, const int64_t* row_start,
+                              int64_t* out_row, int64_t* out_col, void* stream);
+
+/* data/mot_graph.py:211, :299-303  F.pairwise_distance(reid[row], reid[col])
+ * out[e] = || reid[row[e]] - reid[col[e]] + 1e-6 ||_2, fp32, fixed summation order. */
+int mpn_pair_reid_dist(const float* reid, int64_t num_nodes, int64_t dim,
+                       const int64_t* row, const int64_t* col, int64_t num_pairs,
+                       float* out, void* stream);
+
+/* utils/graph.py:40-87  get_knn_mask(pwise_dist, edge_ixs, num_nodes, top_k_nns, ..,
+ *                                    reciprocal_k_nns, symmetric_edges)
+ * keep[e] = in_k(row,col) AND/OR in_k(col,row); in_k(i,j) <=> j is among the top_k
+ * entries of the ascending, index-stable sort of dense row i (missing pairs = +inf).
+ * workspace: num_nodes*num_nodes floats + 2*num_nodes*8 bytes (mpn_knn_mask_workspace). */
+int64_t mpn_knn_mask_workspace(int64_t num_nodes);
+int mpn_knn_mask(const float* pwise_dist, const int64_t* row, const int64_t* col,
+                 int64_t num_edges, int64_t num_nodes, int64_t top_k, int reciprocal,
+                 int symmetric_edges, void* workspace, uint8_t* keep, void* stream);
+
+/* Order-preserving compaction of pairs by a keep mask (edge_ixs.T[mask].T,
+ * data/mot_graph.py:219; tracker/mpn_tracker.py:111-112).  SYNCS to return *h_kept.
+ * scan_ws: (num_edges+1) int64. in/out may not alias. */
+int mpn_compact_pairs(const int64_t* row, const int64_t* col, const float* dist,
+                      const uint8_t* keep, int64_t num_edges, int64_t* scan_ws,
+                      int64_t* out_row, int64_t* out_col, float* out_dist,
+                      int64_t* h_kept, void* stream);
+
+/* utils/graph.py:90-124 compute_edge_feats_dict + data/mot_graph.py:292-312 assembly.
+ * For each undirected pair p (row<col) writes the feature row
+ *   [dt, dx/hbar, dy/hbar, log(h_col/h_row), log(w_col/w_row), reid_dist]
+ * to edge_attr[p] and edge_attr[p + num_pairs] (both directions share the row), and
+ * edge_index = [ (row,col) ... , (col,row) ... ]  ([2, 2*num_pairs] int64).
+ * frame is given as fp32 seconds numerator: secs = frame_f32 / fps. reid_dist may be
+ * NULL (then 5 columns are written, attr_dim must be 5). */
+int mpn_edge_feats_assemble(const int64_t* row, const int64_t* col, int64_t num_pairs,
+                            const float* frame_f32, const float* bb_height,
+                            const float* bb_width, const float* feet_x, const float* feet_y,
+                            float fps, const float* reid_dist, int64_t attr_dim,
+                            float* edge_attr /*[2P, attr_dim]*/, int64_t* edge_index /*[2,2P]*/,
+                            void* stream);
+
+/* ------------------------------------------------------------------ model: layout */
+
+/* Internal edge layout for the fused message-passing kernels ("slots"): directed edges
+ * with row<col (the flow_out set, models/mpn.py:85) first, then those with row>col (the
+ * flow_in set, models/mpn.py:91), each group sorted by row, original order kept inside a
+ * row (stable), so that per-node aggregation is a contiguous, deterministic segment.
+ *   slot_row/slot_col [E] int32, slot_edge [E] int32 (slot -> original edge id),
+ *   out_ptr/in_ptr [N+1] int32 slot ranges per node; *h_num_out = #edges with row<col.
+ * workspace bytes: mpn_edge_layout_workspace(E, N).  SYNCS (one 8-byte read). */
+int64_t mpn_edge_layout_workspace(int64_t num_edges, int64_t num_nodes);
+int mpn_edge_layout_build(const int64_t* edge_index /*[2,E]*/, int64_t num_edges,
+                          int64_t num_nodes, void* workspace, int32_t* slot_row,
+                          int32_t* slot_col, int32_t* slot_edge, int32_t* out_ptr,
+                          int32_t* in_ptr, int64_t* h_num_out, void* stream);
+
+/* ------------------------------------------------------------------ model: encoders */
+
+/* models/mpn.py:351-352  AdaptiveAvgPool2d((1,1)) + view: x[N,C,HW] -> out[N,C]. */
+int mpn_avgpool(const float* x, int64_t n, int64_t c, int64_t hw, float* out, void* stream);
+
+/* models/mlp.py:12-23  one Linear(+ReLU) layer: out[M,O] = act(in[M,K] @ W[O,K]^T + b). */
+int mpn_linear(const float* in, int64_t m, int64_t k, const float* w, const float* b,
+               int64_t o, int relu, float* out, void* stream);
+
+/* out[r] = in[idx[r]] for rows of `width` floats (edge_attr[slot_edge] for non-default
+ * encoder widths, where the fused edge encoder below does not apply). */
+int mpn_gather_rows(const float* in, const int32_t* idx, int64_t rows, int64_t width, float* out,
+                    void* stream);
+
+/* models/mpn.py:355 encoder.edge_model on edge_attr rows taken in slot order:
+ * e_init[s] = MLP(edge_attr[slot_edge[s]]), widths dims[0..n_layers] (ReLU after every
+ * layer whose width != 1).  weights[l] is W_l [dims[l+1], dims[l]], biases[l] [dims[l+1]]
+ * (host arrays of device pointers).  Supported: dims[l] <= 32. */
+int mpn_edge_encoder(const float* edge_attr, const int32_t* slot_edge, int64_t num_edges,
+                     const int32_t* h_dims, int32_t n_layers, const float* const* h_weights,
+                     const float* const* h_biases, float* e_init, void* stream);
+
+/* ------------------------------------------------------------------ model: message passing */
+
+/* Weights of the core network, plain nn.Linear layout W[out,in] (device pointers).
+ * models/mpn.py:275-317, configs/tracking_cfg.yaml:134-168. */
+typedef struct {
+  int32_t dn;        /* node latent width (32)  */
+  int32_t de;        /* edge latent width (16)  */
+  int32_t edge_h;    /* edge MLP hidden (80)    */
+  int32_t flow_h;    /* flow MLP hidden (56)    */
+  int32_t cls_h;     /* classifier hidden (8)   */
+  const float* edge_w0;  const float* edge_b0;   /* [edge_h, 4*dn+2*de]           */
+  const float* edge_w1;  const float* edge_b1;   /* [de, edge_h]                  */
+  const float* fin_w0;   const float* fin_b0;    /* flow_in  [flow_h, 2*dn+de]    */
+  const float* fin_w1;   const float* fin_b1;    /* flow_in  [dn, flow_h]         */
+  const float* fout_w0;  const float* fout_b0;   /* flow_out [flow_h, 2*dn+de]    */
+  const float* fout_w1;  const float* fout_b1;   /* flow_out [dn, flow_h]         */
+  const float* node_w;   const float* node_b;    /* [dn, 2*dn]                    */
+  const float* cls_w0;   const float* cls_b0;    /* [cls_h, de]                   */
+  const float* cls_w1;   const float* cls_b1;    /* [1, cls_h]                    */
+} mpn_core_weights;
+
+typedef struct {
+  int64_t num_nodes, num_edges, num_out;        /* num_out = #slots of the flow_out group */
+  const int32_t* slot_row; const int32_t* slot_col; const int32_t* slot_edge;
+  const int32_t* out_ptr;  const int32_t* in_ptr;
+} mpn_edge_layout;
+
+/* Bytes of scratch mpn_mp_forward needs (node state ping-pong, edge state ping-pong,
+ * flow sums, tile partials). */
+int64_t mpn_mp_workspace(int64_t num_nodes, int64_t num_edges);
+
+/* models/mpn.py:33-54 MetaLayer.forward as ONE step on explicit latent states:
+ *   mode 3: edge update then node update; mode 1: EdgeModel.forward only (:67-69, writes
+ *   e_out); mode 2: TimeAwareNodeModel.forward only (:83-99, e_lat is taken as the already
+ *   updated edge features, writes x_out).  logits (original edge order, may be NULL) gets
+ *   classifier(e') (:114).  All edge tensors are in slot order. e_out may alias e_lat. */
+int mpn_mp_step(const mpn_core_weights* h_w, const mpn_edge_layout* h_g, const float* x_init,
+                const float* x_lat, const float* e_init, const float* e_lat, int32_t mode,
+                void* workspace, float* e_out, float* x_out, float* logits, void* stream);
+
+/* models/mpn.py:364-381  the step loop: num_steps x { reattach, MetaLayer.forward
+ * (EdgeModel :67-69, TimeAwareNodeModel :83-99), classifier :114 }.
+ *   x_init [N,dn], e_init [E,de] (slot order)   -- encoder outputs (models/mpn.py:355-360)
+ *   logits [num_class_steps, E] in ORIGINAL edge order: step s (1-based) is written to
+ *          row s - first_class_step when s >= first_class_step (models/mpn.py:364,379-381);
+ *          num_steps == 0 writes classifier(e_init) to row 0 (models/mpn.py:387-389).
+ *   x_out [N,dn], e_out [E,de] (slot order) final latent states (may be NULL). */
+int mpn_mp_forward(const mpn_core_weights* h_w, const mpn_edge_layout* h_g,
+                   const float* x_init, const float* e_init, int32_t num_steps,
+                   int32_t first_class_step, void* workspace, float* logits,
+                   float* x_out, float* e_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPNTRACK_B200_H */

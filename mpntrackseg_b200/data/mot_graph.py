@@ -1,0 +1,139 @@
+"""``Graph`` attribute bag and ``MOTGraph`` edge construction / assembly on the GPU.
+reference: src/mot_neural_solver/data/mot_graph.py (Graph :21-83, _get_edge_ixs :195-221,
+construct_graph_object :283-316).
+
+The reference's ``Graph`` derives from torch_geometric's ``Data``; only the attribute-bag
+behaviour and ``num_nodes`` / ``num_edges`` are used on the hot path, so this one is a plain
+object.  ``MOTGraph`` here takes the detection table and the already-loaded appearance
+tensors (disk IO of the per-frame ``.pt`` files is outside the hot path).
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+_DATA_ATTRS = ('x', 'x_ext', 'edge_attr', 'edge_index', 'mask_attr', 'node_names', 'edge_labels',
+               'edge_preds', 'reid_emb_dists')
+
+
+class Graph(object):
+    """reference: data/mot_graph.py:21-83"""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+    @property
+    def num_edges(self):
+        return self.edge_index.size(1)
+
+    def _change_attrs_types(self, attr_change_fn):
+        for name in _DATA_ATTRS:
+            val = getattr(self, name, None)
+            if val is not None:
+                setattr(self, name, attr_change_fn(val))
+
+    def tensor(self):
+        self._change_attrs_types(torch.tensor)
+        return self
+
+    def float(self):
+        self._change_attrs_types(lambda t: t.float())
+        return self
+
+    def numpy(self):
+        self._change_attrs_types(lambda t: t if isinstance(t, np.ndarray) else t.detach().cpu().numpy())
+        return self
+
+    def cpu(self):
+        self._change_attrs_types(lambda t: t.cpu())
+        return self
+
+    def cuda(self):
+        self._change_attrs_types(lambda t: t.cuda())
+        return self
+
+    def to(self, device):
+        self._change_attrs_types(lambda t: t.to(device))     # in place, returns None (mot_graph.py:76-77)
+
+    def device(self):
+        if isinstance(getattr(self, 'edge_index', None), torch.Tensor):
+            return self.edge_index.device
+        return torch.device('cpu')
+
+
+def _col(table, name, dev):
+    v = table[name]
+    if torch.is_tensor(v):
+        return v.to(dev)
+    v = v.values if hasattr(v, 'values') else v
+    return torch.as_tensor(np.asarray(v)).to(dev)
+
+
+class MOTGraph(object):
+    """Edge construction + Graph assembly for one frame window.
+
+    graph_df: detection table (DataFrame or dict of arrays) with columns frame, bb_height,
+    bb_width, feet_x, feet_y, rows sorted by (frame, detection_id) (mot_graph.py:145).
+    reid_embeddings [N,256], node_core_feats [N,2048,8,4], node_ext_feats [N,256,14,14]: what
+    ``_load_appearance_data`` returns in the reference (mot_graph.py:153-193).
+    """
+
+    def __init__(self, graph_df, reid_embeddings, node_core_feats, node_ext_feats=None, seq_info_dict=None,
+                 dataset_params=None, inference_mode=False, max_frame_dist=None):
+        self.graph_df = graph_df
+        self.seq_info_dict = seq_info_dict or {}
+        self.dataset_params = dataset_params
+        self.inference_mode = inference_mode
+        self.max_frame_dist = max_frame_dist if max_frame_dist is not None else dataset_params['max_frame_dist']
+        self.device = torch.device('cuda')
+        self.reid_embeddings = reid_embeddings.to(self.device, torch.float32)
+        self.node_core_feats = node_core_feats
+        self.node_ext_feats = node_ext_feats
+        self.graph_obj = None
+
+    def _get_edge_ixs(self, reid_embeddings):
+        """Time-valid pairs, pruned to reciprocal top-k ReID neighbours in training mode.
+        Returns (pairs [2,P] int64 on the GPU, reid distance per pair or None).
+        reference: data/mot_graph.py:195-221"""
+        frame = _col(self.graph_df, 'frame', self.device).to(torch.int64)
+        mfd = self.max_frame_dist
+        pairs = ops.time_valid_pairs(frame, -1 if mfd == 'max' else int(mfd))
+        dist = None
+        k = self.dataset_params['top_k_nns']
+        if not self.inference_mode and k is not None:
+            dist = ops.pair_reid_dist(reid_embeddings, pairs)
+            keep = ops.knn_mask(dist, pairs, frame.numel(), k, self.dataset_params['reciprocal_k_nns'],
+                                symmetric_edges=False)
+            pairs, dist = ops.compact_pairs(pairs, keep, dist)
+        return pairs, dist
+
+    def construct_graph_object(self):
+        """reference: data/mot_graph.py:283-316"""
+        dev = self.device
+        pairs, dist = self._get_edge_ixs(self.reid_embeddings)
+        if dist is None:
+            dist = ops.pair_reid_dist(self.reid_embeddings, pairs)
+        use = self.dataset_params['edge_feats_to_use']
+        cols = {n: _col(self.graph_df, n, dev).float() for n in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+        with_dist = 'emb_dist' in use
+        attr, edge_index = ops.edge_feats_assemble(pairs, cols['frame'], cols['bb_height'], cols['bb_width'],
+                                                   cols['feet_x'], cols['feet_y'], self.seq_info_dict['fps'],
+                                                   dist if with_dist else None)
+        order = ('secs_time_dists', 'norm_feet_x_dists', 'norm_feet_y_dists', 'bb_height_dists',
+                 'bb_width_dists', 'emb_dist')
+        wanted = [order.index(n) for n in use if n in order and (n != 'emb_dist')]
+        if with_dist:
+            wanted.append(5)                                   # emb_dist is appended last (mot_graph.py:306-307)
+        if wanted != list(range(attr.shape[1])):
+            attr = attr[:, wanted].contiguous()
+        self.graph_obj = Graph(x=self.node_core_feats, x_ext=self.node_ext_feats, edge_attr=attr,
+                               edge_index=edge_index)
+        if self.inference_mode:
+            self.graph_obj.reid_emb_dists = torch.cat((dist, dist))
+        self.graph_obj.to(dev)
+        return self.graph_obj

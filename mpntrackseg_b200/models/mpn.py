@@ -1,0 +1,238 @@
+"""Drop-in ``MOTMPNet`` / ``MetaLayer`` with the reference's constructors, parameter names
+and ``forward`` signatures, evaluated by the sm_100a kernels of libmpntrack_b200.so.
+
+reference: src/mot_neural_solver/models/mpn.py (MetaLayer :11-57, EdgeModel :59-69,
+TimeAwareNodeModel :71-99, MLPGraphIndependent :139-178, MOTMPNet :209-394).
+
+The modules own ``nn.Parameter``s exactly where the reference does (so ``state_dict`` keys
+match and its checkpoints load), and hand raw device pointers to the C ABI.  There is no
+CPU path: CPU tensors raise.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from ..config import core_dims
+from .mlp import MLP
+
+
+def _core_weight_tensors(edge_mlp, flow_in, flow_out, node_lin, cls_mlp):
+    e0, e1 = edge_mlp.linears()
+    i0, i1 = flow_in.linears()
+    o0, o1 = flow_out.linears()
+    c0, c1 = cls_mlp.linears()
+    return {'edge_w0': e0.weight, 'edge_b0': e0.bias, 'edge_w1': e1.weight, 'edge_b1': e1.bias,
+            'fin_w0': i0.weight, 'fin_b0': i0.bias, 'fin_w1': i1.weight, 'fin_b1': i1.bias,
+            'fout_w0': o0.weight, 'fout_b0': o0.bias, 'fout_w1': o1.weight, 'fout_b1': o1.bias,
+            'node_w': node_lin.weight, 'node_b': node_lin.bias,
+            'cls_w0': c0.weight, 'cls_b0': c0.bias, 'cls_w1': c1.weight, 'cls_b1': c1.bias}
+
+
+class _NullClassifier(nn.Module):
+    """Zero classifier used when MetaLayer is called standalone (no logits wanted)."""
+
+    def __init__(self, de, device):
+        super().__init__()
+        self.l0 = nn.Linear(de, 8).to(device)
+        self.l1 = nn.Linear(8, 1).to(device)
+
+    def linears(self):
+        return [self.l0, self.l1]
+
+
+class EdgeModel(nn.Module):
+    """Edge update e' = MLP(cat[x[row], x[col], e]).  reference: models/mpn.py:59-69"""
+
+    def __init__(self, edge_model):
+        super().__init__()
+        self.edge_model = edge_model
+
+    def forward(self, node_feats, edge_index, edge_attr):
+        raise NotImplementedError('EdgeModel is evaluated inside MetaLayer.forward (fused kernel); '
+                                  'call MetaLayer(edge_model=..., node_model=None)')
+
+
+class TimeAwareNodeModel(nn.Module):
+    """Time-aware node update.  reference: models/mpn.py:71-99"""
+
+    def __init__(self, flow_in_model, flow_out_model, node_model, node_agg_fn):
+        super().__init__()
+        self.flow_in_model = flow_in_model
+        self.flow_out_model = flow_out_model
+        self.node_model = node_model
+        self.node_agg_fn = node_agg_fn
+
+    def forward(self, x, edge_index, edge_attr):
+        raise NotImplementedError('TimeAwareNodeModel is evaluated inside MetaLayer.forward (fused kernel); '
+                                  'call MetaLayer(edge_model=None, node_model=...)')
+
+
+class MetaLayer(nn.Module):
+    """One message-passing step ``forward(x, edge_index, edge_attr) -> (x', edge_attr')`` with
+    x = [x_init | x_latent], edge_attr = [e_init | e_latent] in the caller's edge order.
+    reference: models/mpn.py:11-57"""
+
+    def __init__(self, edge_model=None, node_model=None):
+        super().__init__()
+        self.edge_model = edge_model
+        self.node_model = node_model
+        self._null_cls = None
+
+    def _weights(self, classifier=None):
+        em, nm = self.edge_model, self.node_model
+        if em is None or nm is None:
+            raise NotImplementedError('the fused step needs both an EdgeModel and a TimeAwareNodeModel')
+        if classifier is None:
+            if self._null_cls is None:
+                dev = em.edge_model.linears()[0].weight.device
+                self._null_cls = [_NullClassifier(em.edge_model.linears()[-1].out_features, dev)]
+            classifier = self._null_cls[0]
+        named = _core_weight_tensors(em.edge_model, nm.flow_in_model, nm.flow_out_model,
+                                     nm.node_model[0], classifier)
+        return ops.core_weights(named)
+
+    def forward(self, x, edge_index, edge_attr):
+        cw, keep = self._weights()
+        dn, de = cw.dn, cw.de
+        if x.shape[1] != 2 * dn or edge_attr.shape[1] != 2 * de:
+            raise NotImplementedError('fused step is built for reattach_initial_nodes/edges = True '
+                                      f'(x [N,{2 * dn}], edge_attr [E,{2 * de}])')
+        layout = ops.edge_layout(edge_index, x.shape[0])
+        e = layout.num_edges
+        ea = ops.gather_rows(edge_attr, layout.slot_edge[:e]) if e else edge_attr
+        e_new, x_new, _ = ops.mp_step(cw, layout, x[:, :dn].contiguous(), x[:, dn:].contiguous(),
+                                      ea[:, :de].contiguous(), ea[:, de:].contiguous(), mode=3)
+        out_e = torch.empty_like(e_new)
+        out_e[layout.slot_edge[:e].long()] = e_new          # back to the caller's edge order
+        del keep
+        return x_new, out_e
+
+    def __repr__(self):
+        return '{}(edge_model={}, node_model={})'.format(self.__class__.__name__, self.edge_model, self.node_model)
+
+
+class MLPGraphIndependent(nn.Module):
+    """Independent node / edge MLPs (encoder, classifier).  reference: models/mpn.py:139-178"""
+
+    def __init__(self, edge_in_dim=None, node_in_dim=None, edge_out_dim=None, node_out_dim=None,
+                 node_dims=None, edge_dims=None, dropout_p=None, use_batchnorm=None):
+        super().__init__()
+        if node_in_dim is not None:
+            self.node_model = MLP(input_dim=node_in_dim, fc_dims=list(node_dims) + [node_out_dim],
+                                  dropout_p=dropout_p, use_batchnorm=use_batchnorm)
+        else:
+            self.node_model = None
+        if edge_in_dim is not None:
+            self.edge_model = MLP(input_dim=edge_in_dim, fc_dims=list(edge_dims) + [edge_out_dim],
+                                  dropout_p=dropout_p, use_batchnorm=use_batchnorm)
+        else:
+            self.edge_model = None
+
+    def forward(self, edge_feats=None, nodes_feats=None):
+        out_node = self.node_model(nodes_feats) if self.node_model is not None else nodes_feats
+        out_edge = self.edge_model(edge_feats) if self.edge_model is not None else edge_feats
+        return out_edge, out_node
+
+
+class MOTMPNet(nn.Module):
+    """Encoder -> ``num_enc_steps`` shared-weight message-passing steps -> edge classifier.
+
+    ``forward(data)`` takes any object with ``x [N,2048,8,4]`` (or pooled ``[N,2048]`` /
+    ``[N,2048,1,1]``), ``edge_index [2,E] int64``, ``edge_attr [E,6]`` (and ``x_ext`` for the
+    mask branch) and returns ``{'classified_edges': [Tensor[E,1]]*num_class_steps,
+    'mask_predictions': [...]}`` like the reference.  reference: models/mpn.py:209-394
+    """
+
+    def __init__(self, model_params, bb_encoder=None):
+        super().__init__()
+        self.node_cnn = bb_encoder
+        self.model_params = model_params
+        enc = model_params['encoder_feats_dict']
+        self.encoder = MLPGraphIndependent(**enc)
+        self.classifier = MLPGraphIndependent(**model_params['classifier_feats_dict'])
+        self.MPNet = self._build_core_MPNet(model_params=model_params, encoder_feats_dict=enc)
+        self.num_enc_steps = model_params['num_enc_steps']
+        self.num_class_steps = model_params['num_class_steps']
+
+    def _build_core_MPNet(self, model_params, encoder_feats_dict):
+        """reference: models/mpn.py:250-317"""
+        agg = model_params['node_agg_fn']
+        assert agg.lower() in ('mean', 'max', 'sum'), "node_agg_fn can only be 'max', 'mean' or 'sum'."
+        if agg != 'sum':
+            raise NotImplementedError("node_agg_fn other than 'sum' is not built into the fused kernel")
+        self.reattach_initial_nodes = model_params['reattach_initial_nodes']
+        self.reattach_initial_edges = model_params['reattach_initial_edges']
+        if not (self.reattach_initial_nodes and self.reattach_initial_edges):
+            raise NotImplementedError('the fused kernel is built for reattach_initial_nodes/edges = True')
+        self.edge_factor, self.node_factor = 2, 2
+        d = core_dims(model_params)
+        em, nm = model_params['edge_model_feats_dict'], model_params['node_model_feats_dict']
+        edge_model = MLP(input_dim=d['edge_mlp_in'], fc_dims=em['dims'], dropout_p=em['dropout_p'],
+                         use_batchnorm=em['use_batchnorm'])
+        flow_in_model = MLP(input_dim=d['flow_mlp_in'], fc_dims=nm['dims'], dropout_p=nm['dropout_p'],
+                            use_batchnorm=nm['use_batchnorm'])
+        flow_out_model = MLP(input_dim=d['flow_mlp_in'], fc_dims=nm['dims'], dropout_p=nm['dropout_p'],
+                             use_batchnorm=nm['use_batchnorm'])
+        node_model = nn.Sequential(nn.Linear(2 * d['dn'], d['dn']), nn.ReLU(inplace=True))
+        return MetaLayer(edge_model=EdgeModel(edge_model=edge_model),
+                         node_model=TimeAwareNodeModel(flow_in_model=flow_in_model, flow_out_model=flow_out_model,
+                                                       node_model=node_model, node_agg_fn=agg))
+
+    # ------------------------------------------------------------------ forward
+    def core_weights(self):
+        return self.MPNet._weights(self.classifier.edge_model)
+
+    def encode_nodes(self, x):
+        """Global average pool + node MLP.  reference: models/mpn.py:351-355"""
+        return self.encoder.node_model(ops.avgpool(x) if x.dim() > 2 else x)
+
+    def encode_edges(self, edge_attr, layout):
+        lins = self.encoder.edge_model.linears()
+        return ops.edge_encoder(edge_attr, layout, [l.weight for l in lins], [l.bias for l in lins])
+
+    def forward_batch(self, graphs):
+        """Extension (not in the reference): evaluate several independent window graphs as one
+        block-diagonal batch (what torch_geometric's DataLoader does with batch_size > 1):
+        nodes are encoded per graph, edge indices are offset by the cumulative node count, and
+        one message-passing run covers all of them.  Returns one output dict per graph."""
+        x0s, eis, eas, sizes, off = [], [], [], [], 0
+        for g in graphs:
+            x0 = self.encode_nodes(g.x)
+            x0s.append(x0)
+            eis.append(g.edge_index + off)
+            eas.append(g.edge_attr)
+            sizes.append((x0.shape[0], g.edge_index.shape[1]))
+            off += x0.shape[0]
+        x0 = torch.cat(x0s)
+        edge_index = torch.cat(eis, dim=1)
+        layout = ops.edge_layout(edge_index, off)
+        e0 = self.encode_edges(torch.cat(eas), layout)
+        cw, keep = self.core_weights()
+        first_class_step = self.num_enc_steps - self.num_class_steps + 1
+        logits = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step)
+        outs, eo = [], 0
+        for _, e in sizes:
+            outs.append({'classified_edges': [logits[i, eo:eo + e].view(-1, 1) for i in range(logits.shape[0])],
+                         'mask_predictions': []})
+            eo += e
+        del keep
+        return outs
+
+    def forward(self, data, return_state=False):
+        x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('backward through the CUDA kernels is not wired yet: call under '
+                                      'torch.no_grad() (as MPNTracker does, tracker/mpn_tracker.py:122)')
+        x0 = self.encode_nodes(x)
+        layout = ops.edge_layout(edge_index, x0.shape[0])
+        e0 = self.encode_edges(edge_attr, layout)
+        cw, keep = self.core_weights()
+        first_class_step = self.num_enc_steps - self.num_class_steps + 1
+        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, want_state=return_state)
+        logits = res[0] if return_state else res
+        out = {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])],
+               'mask_predictions': []}
+        if return_state:
+            out['node_state'], out['edge_state_slots'], out['layout'] = res[1], res[2], layout
+        del keep
+        return out

@@ -1,0 +1,253 @@
+"""Tensor-level wrappers over the C ABI (include/mpntrack_b200.h).
+
+Each function validates device / dtype / contiguity, allocates outputs with torch (device
+memory + stream plumbing only) and enqueues the library's kernels on torch's current
+stream.  CPU tensors are rejected: there is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _cabi
+from ._cabi import CoreWeights, EdgeLayout, check, lib, ptr, stream_ptr
+
+
+def _req(t, dtype, name):
+    if not torch.is_tensor(t):
+        raise TypeError(f'{name}: expected a torch tensor, got {type(t).__name__}')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: must be a CUDA tensor (no CPU fallback)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _bytes(n, device):
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ graph construction
+def time_valid_pairs(frame_num, max_frame_dist=-1, node_graph_ptr=None):
+    """[2, E_c] int64 candidate pairs (i<j), sorted by (i, j).  utils/graph.py:6-37"""
+    f = _req(frame_num, torch.int64, 'frame_num')
+    n = f.numel()
+    gp = None if node_graph_ptr is None else _req(node_graph_ptr, torch.int64, 'node_graph_ptr')
+    g = 0 if gp is None else gp.numel() - 1
+    row_start = torch.empty(n + 1, dtype=torch.int64, device=f.device)
+    total = C.c_int64(0)
+    check(lib().mpn_time_valid_pairs_count(ptr(f), n, ptr(gp), g, int(max_frame_dist), ptr(row_start),
+                                           C.byref(total), stream_ptr()), 'time_valid_pairs_count')
+    pairs = torch.empty((2, total.value), dtype=torch.int64, device=f.device)
+    check(lib().mpn_time_valid_pairs_fill(ptr(f), n, ptr(gp), g, int(max_frame_dist), ptr(row_start),
+                                          ptr(pairs[0]), ptr(pairs[1]), stream_ptr()), 'time_valid_pairs_fill')
+    return pairs
+
+
+def pair_reid_dist(reid, pairs):
+    """[E] fp32 ||a-b+1e-6||_2.  data/mot_graph.py:211,299-303"""
+    reid = _req(reid, torch.float32, 'reid')
+    pairs = _req(pairs, torch.int64, 'pairs')
+    e = pairs.shape[1]
+    out = torch.empty(e, dtype=torch.float32, device=reid.device)
+    check(lib().mpn_pair_reid_dist(ptr(reid), reid.shape[0], reid.shape[1], ptr(pairs[0]), ptr(pairs[1]),
+                                   e, ptr(out), stream_ptr()), 'pair_reid_dist')
+    return out
+
+
+def knn_mask(pwise_dist, edge_ixs, num_nodes, top_k, reciprocal, symmetric_edges):
+    """bool [E'] keep mask.  utils/graph.py:40-87"""
+    d = _req(pwise_dist.view(-1), torch.float32, 'pwise_dist')
+    ei = _req(edge_ixs, torch.int64, 'edge_ixs')
+    e = ei.shape[1]
+    if d.numel() != e:
+        raise ValueError(f'pwise_dist has {d.numel()} entries for {e} edges')
+    ws = _bytes(lib().mpn_knn_mask_workspace(int(num_nodes)), d.device)
+    keep = torch.empty(e, dtype=torch.uint8, device=d.device)
+    check(lib().mpn_knn_mask(ptr(d), ptr(ei[0]), ptr(ei[1]), e, int(num_nodes), int(top_k), int(bool(reciprocal)),
+                             int(bool(symmetric_edges)), ptr(ws), ptr(keep), stream_ptr()), 'knn_mask')
+    return keep.view(torch.bool)
+
+
+def compact_pairs(pairs, keep, dist=None):
+    """pairs[:, keep] (and dist[keep]) in order.  data/mot_graph.py:219"""
+    pairs = _req(pairs, torch.int64, 'pairs')
+    k8 = _req(keep.view(torch.uint8) if keep.dtype == torch.bool else keep, torch.uint8, 'keep')
+    e = pairs.shape[1]
+    scan = torch.empty(e + 1, dtype=torch.int64, device=pairs.device)
+    out = torch.empty_like(pairs)
+    od = torch.empty_like(dist) if dist is not None else None
+    kept = C.c_int64(0)
+    check(lib().mpn_compact_pairs(ptr(pairs[0]), ptr(pairs[1]), ptr(dist), ptr(k8), e, ptr(scan), ptr(out[0]),
+                                  ptr(out[1]), ptr(od), C.byref(kept), stream_ptr()), 'compact_pairs')
+    k = kept.value
+    # out rows are contiguous slabs of length e; re-pack to [2, k]
+    res = torch.stack((out[0, :k], out[1, :k]))
+    return (res, od[:k]) if dist is not None else res
+
+
+def edge_feats_assemble(pairs, frame_f32, bb_height, bb_width, feet_x, feet_y, fps, reid_dist):
+    """(edge_attr [2P, 5|6] fp32, edge_index [2, 2P] int64).
+    utils/graph.py:90-124 + data/mot_graph.py:292-312"""
+    pairs = _req(pairs, torch.int64, 'pairs')
+    p = pairs.shape[1]
+    cols = [_req(t, torch.float32, n) for t, n in ((frame_f32, 'frame'), (bb_height, 'bb_height'),
+                                                    (bb_width, 'bb_width'), (feet_x, 'feet_x'), (feet_y, 'feet_y'))]
+    ad = 6 if reid_dist is not None else 5
+    rd = None if reid_dist is None else _req(reid_dist.view(-1), torch.float32, 'reid_dist')
+    attr = torch.empty((2 * p, ad), dtype=torch.float32, device=pairs.device)
+    eidx = torch.empty((2, 2 * p), dtype=torch.int64, device=pairs.device)
+    check(lib().mpn_edge_feats_assemble(ptr(pairs[0]), ptr(pairs[1]), p, *[ptr(c) for c in cols], float(fps),
+                                        ptr(rd), ad, ptr(attr), ptr(eidx), stream_ptr()), 'edge_feats_assemble')
+    return attr, eidx
+
+
+# ------------------------------------------------------------------ layout
+@dataclass
+class Layout:
+    num_nodes: int
+    num_edges: int
+    num_out: int
+    slot_row: torch.Tensor
+    slot_col: torch.Tensor
+    slot_edge: torch.Tensor
+    out_ptr: torch.Tensor
+    in_ptr: torch.Tensor
+
+    def c_struct(self):
+        return EdgeLayout(self.num_nodes, self.num_edges, self.num_out, self.slot_row.data_ptr(),
+                          self.slot_col.data_ptr(), self.slot_edge.data_ptr(), self.out_ptr.data_ptr(),
+                          self.in_ptr.data_ptr())
+
+
+def edge_layout(edge_index, num_nodes):
+    """Slot layout (flow_out group then flow_in group, row-sorted, stable)."""
+    ei = _req(edge_index, torch.int64, 'edge_index')
+    if ei.dim() != 2 or ei.shape[0] != 2:
+        raise ValueError(f'edge_index must be [2, E], got {tuple(ei.shape)}')
+    e, n, dev = ei.shape[1], int(num_nodes), ei.device
+    ws = _bytes(lib().mpn_edge_layout_workspace(e, n), dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    srow, scol, sedge = (torch.empty(max(e, 1), **i32) for _ in range(3))
+    optr, iptr = torch.empty(n + 1, **i32), torch.empty(n + 1, **i32)
+    num_out = C.c_int64(0)
+    check(lib().mpn_edge_layout_build(ptr(ei), e, n, ptr(ws), ptr(srow), ptr(scol), ptr(sedge), ptr(optr),
+                                      ptr(iptr), C.byref(num_out), stream_ptr()), 'edge_layout_build')
+    return Layout(n, e, num_out.value, srow, scol, sedge, optr, iptr)
+
+
+# ------------------------------------------------------------------ encoders
+def avgpool(x):
+    """[N, C, H, W] -> [N, C].  models/mpn.py:351-352"""
+    x = _req(x, torch.float32, 'x')
+    n, c = x.shape[0], x.shape[1]
+    hw = 1
+    for s in x.shape[2:]:
+        hw *= s
+    if hw == 1:
+        return x.reshape(n, c)
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(lib().mpn_avgpool(ptr(x), n, c, hw, ptr(out), stream_ptr()), 'avgpool')
+    return out
+
+
+def linear(inp, weight, bias, relu):
+    """act(inp @ weight.T + bias).  models/mlp.py:12-23"""
+    inp = _req(inp, torch.float32, 'input')
+    w = _req(weight, torch.float32, 'weight')
+    b = None if bias is None else _req(bias, torch.float32, 'bias')
+    m, k = inp.shape
+    o = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError(f'linear: input has {k} columns, weight expects {w.shape[1]}')
+    out = torch.empty((m, o), dtype=torch.float32, device=inp.device)
+    check(lib().mpn_linear(ptr(inp), m, k, ptr(w), ptr(b), o, int(bool(relu)), ptr(out), stream_ptr()), 'linear')
+    return out
+
+
+def gather_rows(inp, idx):
+    inp = _req(inp, torch.float32, 'input')
+    idx = _req(idx, torch.int32, 'idx')
+    rows, width = idx.numel(), inp.shape[1]
+    out = torch.empty((rows, width), dtype=torch.float32, device=inp.device)
+    check(lib().mpn_gather_rows(ptr(inp), ptr(idx), rows, width, ptr(out), stream_ptr()), 'gather_rows')
+    return out
+
+
+def edge_encoder(edge_attr, layout, weights, biases):
+    """e_init in slot order.  models/mpn.py:355 (encoder.edge_model)"""
+    attr = _req(edge_attr, torch.float32, 'edge_attr')
+    ws = [_req(w, torch.float32, 'weight') for w in weights]
+    bs = [_req(b, torch.float32, 'bias') for b in biases]
+    dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+    e = layout.num_edges
+    if attr.shape != (e, dims[0]):
+        raise ValueError(f'edge_attr must be [{e}, {dims[0]}], got {tuple(attr.shape)}')
+    if dims == [6, 18, 18, 16]:
+        out = torch.empty((e, dims[-1]), dtype=torch.float32, device=attr.device)
+        cdims = (C.c_int32 * len(dims))(*dims)
+        cw = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        cb = (C.c_void_p * len(bs))(*[b.data_ptr() for b in bs])
+        check(lib().mpn_edge_encoder(ptr(attr), ptr(layout.slot_edge), e, cdims, len(ws), cw, cb, ptr(out),
+                                     stream_ptr()), 'edge_encoder')
+        return out
+    h = gather_rows(attr, layout.slot_edge[:e]) if e else attr.new_empty((0, dims[0]))
+    for w, b in zip(ws, bs):
+        h = linear(h, w, b, relu=w.shape[0] != 1)
+    return h
+
+
+# ------------------------------------------------------------------ message passing
+def core_weights(named):
+    """Build the mpn_core_weights struct from a dict of CUDA fp32 tensors keyed by the struct's
+    field names; returns (struct, keepalive list)."""
+    keep = {k: _req(v, torch.float32, k) for k, v in named.items()}
+    dn = keep['node_w'].shape[0]
+    de = keep['edge_w1'].shape[0]
+    cw = CoreWeights()
+    cw.dn, cw.de = dn, de
+    cw.edge_h, cw.flow_h, cw.cls_h = keep['edge_w0'].shape[0], keep['fin_w0'].shape[0], keep['cls_w0'].shape[0]
+    expect = {'edge_w0': (cw.edge_h, 4 * dn + 2 * de), 'edge_w1': (de, cw.edge_h),
+              'fin_w0': (cw.flow_h, 2 * dn + de), 'fin_w1': (dn, cw.flow_h),
+              'fout_w0': (cw.flow_h, 2 * dn + de), 'fout_w1': (dn, cw.flow_h),
+              'node_w': (dn, 2 * dn), 'cls_w0': (cw.cls_h, de), 'cls_w1': (1, cw.cls_h)}
+    for k, shp in expect.items():
+        if tuple(keep[k].shape) != shp:
+            raise ValueError(f'{k}: expected shape {shp}, got {tuple(keep[k].shape)}')
+    for name, _ in CoreWeights._fields_[5:]:
+        setattr(cw, name, keep[name].data_ptr())
+    return cw, list(keep.values())
+
+
+def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False):
+    """Run the step loop.  Returns logits [S, E] (original edge order) and, if asked, the final
+    node / edge latent states (edge state in slot order).  models/mpn.py:364-389"""
+    x_init = _req(x_init, torch.float32, 'x_init')
+    e_init = _req(e_init, torch.float32, 'e_init')
+    n, e, dev = layout.num_nodes, layout.num_edges, x_init.device
+    n_cls = 1 if num_steps == 0 else max(num_steps - first_class_step + 1, 0)
+    n_cls = min(n_cls, max(num_steps, 1))
+    first = max(first_class_step, 1)
+    logits = torch.empty((n_cls, e), dtype=torch.float32, device=dev)
+    ws = _bytes(lib().mpn_mp_workspace(n, e), dev)
+    x_out = torch.empty((n, cw.dn), dtype=torch.float32, device=dev) if want_state else None
+    e_out = torch.empty((e, cw.de), dtype=torch.float32, device=dev) if want_state else None
+    g = layout.c_struct()
+    check(lib().mpn_mp_forward(C.byref(cw), C.byref(g), ptr(x_init), ptr(e_init), int(num_steps), int(first),
+                               ptr(ws), ptr(logits), ptr(x_out), ptr(e_out), stream_ptr()), 'mp_forward')
+    return (logits, x_out, e_out) if want_state else logits
+
+
+def mp_step(cw, layout, x_init, x_lat, e_init, e_lat, mode=3, want_logits=False):
+    """One MetaLayer step on explicit states (edge tensors in slot order).  models/mpn.py:33-54"""
+    n, e, dev = layout.num_nodes, layout.num_edges, x_init.device
+    args = [_req(t, torch.float32, nm) for t, nm in ((x_init, 'x_init'), (x_lat, 'x_lat'),
+                                                      (e_init, 'e_init'), (e_lat, 'e_lat'))]
+    ws = _bytes(lib().mpn_mp_workspace(n, e), dev)
+    e_out = torch.empty((e, cw.de), dtype=torch.float32, device=dev) if mode & 1 else None
+    x_out = torch.empty((n, cw.dn), dtype=torch.float32, device=dev) if mode & 2 else None
+    logits = torch.empty(e, dtype=torch.float32, device=dev) if want_logits else None
+    g = layout.c_struct()
+    check(lib().mpn_mp_step(C.byref(cw), C.byref(g), *[ptr(t) for t in args], int(mode), ptr(ws), ptr(e_out),
+                            ptr(x_out), ptr(logits), stream_ptr()), 'mp_step')
+    return e_out, x_out, logits

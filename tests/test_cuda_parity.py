@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+outputs of the reference.  Integer / index results must be bit-exact; edge logits within
+the tolerance BASELINE.json states (1e-3 absolute on probabilities, decisions identical
+outside +-1e-3 of 0.5; on raw logits 1e-3 * max(1, |logit|))."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, load_case
+from mpntrackseg_b200 import synth
+from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params
+from oracle import graph_ref, mpn_ref
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def assert_logits_close(got, exp, what=''):
+    got, exp = np.asarray(got, dtype=np.float64), np.asarray(exp, dtype=np.float64)
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    tol = 1e-3 * np.maximum(1.0, np.abs(exp))
+    bad = np.abs(got - exp) > tol
+    assert not bad.any(), f'{what}: {bad.sum()} logits off, max err {np.abs(got - exp).max():.3e}'
+    pg, pe = 1 / (1 + np.exp(-got)), 1 / (1 + np.exp(-exp))
+    assert np.abs(pg - pe).max() <= PROB_TOL, f'{what}: max |dp| {np.abs(pg - pe).max():.3e}'
+    decisive = np.abs(pe - 0.5) > PROB_TOL
+    assert ((pg > 0.5) == (pe > 0.5))[decisive].all(), f'{what}: binarised decisions differ'
+
+
+def make_model(mp, P):
+    from mpntrackseg_b200.models.mpn import MOTMPNet
+    model = MOTMPNet(mp).to(dev()).eval()
+    core = {k: v for k, v in P.items() if k in model.state_dict()}
+    model.load_state_dict(core, strict=True)
+    return model
+
+
+class Data:
+    pass
+
+
+# ------------------------------------------------------------------ graph construction
+@pytest.mark.parametrize('name', list(CASES))
+def test_drop_in_graph_utils_match_oracle(name):
+    from mpntrackseg_b200.utils.graph import compute_edge_feats_dict, get_knn_mask, get_time_valid_conn_ixs
+    c = load_case(name)
+    win, ds = c['win'], c['ds']
+    mfd = c['max_frame_dist']
+    pairs = get_time_valid_conn_ixs(win.frame, mfd, use_cuda=True)
+    ref_pairs = graph_ref.time_valid_pairs(win.frame, mfd)
+    assert pairs.device.type == 'cpu' and pairs.dtype == torch.int64
+    assert torch.equal(pairs, ref_pairs)
+    ref_d = graph_ref.pair_reid_dist(win.reid, ref_pairs)
+    for recip in (True, False):
+        keep = get_knn_mask(ref_d, ref_pairs, win.N, ds['top_k_nns'], use_cuda=True, reciprocal_k_nns=recip,
+                            symmetric_edges=False)
+        ref_keep = graph_ref.knn_keep_mask(ref_d, ref_pairs, win.N, ds['top_k_nns'], recip, symmetric_edges=False)
+        assert keep.dtype == torch.bool and torch.equal(keep.cpu(), ref_keep)
+    feats = compute_edge_feats_dict(ref_pairs, synth.det_columns(win), win.fps, use_cuda=True)
+    ref_f = graph_ref.edge_geometry(ref_pairs, synth.det_columns(win), win.fps)
+    assert set(feats) == set(ref_f)
+    for k in ref_f:
+        np.testing.assert_allclose(feats[k].cpu().numpy(), ref_f[k].numpy(), rtol=2e-6, atol=2e-7, err_msg=k)
+    # differences and quotients are IEEE-exact; only logf may differ in the last ulp
+    for k in ('secs_time_dists', 'norm_feet_x_dists', 'norm_feet_y_dists'):
+        assert torch.equal(feats[k].cpu(), ref_f[k]), k
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_motgraph_matches_reference_golden(name):
+    from mpntrackseg_b200.data.mot_graph import MOTGraph
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, c['ds'],
+                 inference_mode=False, max_frame_dist=c['max_frame_dist']).construct_graph_object()
+    assert g.edge_index.dtype == torch.int64 and g.edge_index.is_cuda
+    assert np.array_equal(g.edge_index.cpu().numpy(), gold['edge_index'].astype(np.int64)), 'KNN edge set'
+    np.testing.assert_allclose(g.edge_attr.cpu().numpy(), gold['edge_attr'], rtol=2e-6, atol=1e-6)
+    assert g.num_nodes == win.N and g.num_edges == gold['edge_index'].shape[1]
+
+
+def test_pair_dist_close_to_torch_formula():
+    from mpntrackseg_b200 import ops
+    win = synth.make_window(T=6, D=20, k=10, seed=9)
+    pairs = graph_ref.time_valid_pairs(win.frame)
+    d = ops.pair_reid_dist(win.reid.to(dev()), pairs.to(dev())).cpu()
+    ref = graph_ref.pair_reid_dist(win.reid, pairs)
+    np.testing.assert_allclose(d.numpy(), ref.numpy(), rtol=3e-6)
+
+
+def test_knn_mask_symmetric_edges_and_ties():
+    """Inference-time call (both directions listed, symmetric_edges=True) incl. k >= degree,
+    exact ties (stable by index) and a batch of windows via node_graph_ptr."""
+    from mpntrackseg_b200 import ops
+    c = load_case('tracker_window')
+    gold, ds = c['gold'], c['ds']
+    win = c['win']
+    ei = torch.from_numpy(gold['full_edge_index'].astype(np.int64))
+    d = torch.from_numpy(gold['full_dists'])
+    for k in (1, 3, 7, 40, 10 ** 6):
+        for recip in (True, False):
+            keep = ops.knn_mask(d.to(dev()), ei.to(dev()), win.N, k, recip, True).cpu()
+            ref = graph_ref.knn_keep_mask(d, ei, win.N, k, recip, True)
+            assert torch.equal(keep, ref), (k, recip)
+    # quantised distances -> many exact ties at the k boundary
+    dq = (d * 2).round() / 2
+    for k in (2, 5):
+        keep = ops.knn_mask(dq.to(dev()), ei.to(dev()), win.N, k, True, True).cpu()
+        assert torch.equal(keep, graph_ref.knn_keep_mask(dq, ei, win.N, k, True, True)), k
+
+
+def test_time_valid_pairs_batched_windows():
+    from mpntrackseg_b200 import ops
+    frames = [torch.arange(1, 5).repeat_interleave(3), torch.arange(10, 13).repeat_interleave(4),
+              torch.tensor([7, 7, 8])]
+    ptr = torch.tensor([0, 12, 24, 27])
+    got = ops.time_valid_pairs(torch.cat(frames).to(dev()), 2, ptr.to(dev())).cpu()
+    exp = torch.cat([graph_ref.time_valid_pairs(f, 2) + int(o) for f, o in zip(frames, ptr[:-1])], dim=1)
+    assert torch.equal(got, exp)
+
+
+def test_tracker_window_prune_and_predict():
+    """mpn_tracker.py:107-135 glue on the CUDA path against the reference's golden output."""
+    from mpntrackseg_b200.data.mot_graph import Graph, MOTGraph
+    from mpntrackseg_b200.utils.graph import get_knn_mask
+    c = load_case('tracker_window')
+    win, gold, ds = c['win'], c['gold'], c['ds']
+    full = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
+                    max_frame_dist=ds['frames_per_graph'] - 1).construct_graph_object()
+    assert np.array_equal(full.edge_index.cpu().numpy(), gold['full_edge_index'].astype(np.int64))
+    np.testing.assert_allclose(full.reid_emb_dists.cpu().numpy(), gold['full_dists'], rtol=3e-6)
+    start, end = (int(v) for v in gold['window'])
+    frame = win.frame.to(dev())
+    nodes_mask = (start <= frame) & (frame <= end)
+    edges_mask = nodes_mask[full.edge_index[0]] & nodes_mask[full.edge_index[1]]
+    first = int(torch.nonzero(nodes_mask)[0])
+    sub = Graph(x=full.x[nodes_mask], x_ext=None, edge_attr=full.edge_attr[edges_mask],
+                reid_emb_dists=full.reid_emb_dists[edges_mask],
+                edge_index=full.edge_index.T[edges_mask].T - first)
+    knn_mask = get_knn_mask(pwise_dist=sub.reid_emb_dists, edge_ixs=sub.edge_index, num_nodes=sub.num_nodes,
+                            top_k_nns=ds['top_k_nns'], use_cuda=True, reciprocal_k_nns=ds['reciprocal_k_nns'],
+                            symmetric_edges=True)
+    assert np.array_equal(knn_mask.cpu().numpy(), gold['keep'])
+    sub.edge_index = sub.edge_index.T[knn_mask].T
+    sub.edge_attr = sub.edge_attr[knn_mask]
+    model = make_model(c['mp'], c['P'])
+    with torch.no_grad():
+        out = model(sub)
+    pruned = torch.sigmoid(out['classified_edges'][-1].view(-1))
+    preds = torch.zeros(knn_mask.shape[0]).to(pruned.device)
+    preds[knn_mask] = pruned
+    assert float((preds.cpu() - torch.from_numpy(gold['edge_preds'])).abs().max()) <= PROB_TOL
+
+
+# ------------------------------------------------------------------ layout
+def test_edge_layout_invariants():
+    from mpntrackseg_b200 import ops
+    c = load_case('config1')
+    ei = torch.from_numpy(c['gold']['edge_index'].astype(np.int64))
+    n, e = c['win'].N, ei.shape[1]
+    # shuffle the edge order: the layout must not rely on the reference's canonical order
+    perm = torch.randperm(e, generator=torch.Generator().manual_seed(0))
+    for edge_index in (ei, ei[:, perm]):
+        lay = ops.edge_layout(edge_index.to(dev()), n)
+        srow, scol, sedge = (t.cpu().long()[:e] for t in (lay.slot_row, lay.slot_col, lay.slot_edge))
+        assert lay.num_out == int((edge_index[0] < edge_index[1]).sum())
+        assert torch.equal(torch.sort(sedge).values, torch.arange(e))                 # a permutation
+        assert torch.equal(edge_index[0][sedge], srow) and torch.equal(edge_index[1][sedge], scol)
+        assert (srow[:lay.num_out] < scol[:lay.num_out]).all() and (srow[lay.num_out:] > scol[lay.num_out:]).all()
+        for a, b in ((0, lay.num_out), (lay.num_out, e)):
+            seg = srow[a:b]
+            assert (seg[1:] >= seg[:-1]).all()
+            same = seg[1:] == seg[:-1]
+            assert (sedge[a:b][1:][same] > sedge[a:b][:-1][same]).all()               # stable inside a row
+        optr, iptr = lay.out_ptr.cpu().long(), lay.in_ptr.cpu().long()
+        assert optr[0] == 0 and optr[-1] == lay.num_out and iptr[0] == lay.num_out and iptr[-1] == e
+        deg_out = torch.bincount(edge_index[0][edge_index[0] < edge_index[1]], minlength=n)
+        deg_in = torch.bincount(edge_index[0][edge_index[0] > edge_index[1]], minlength=n)
+        assert torch.equal(optr[1:] - optr[:-1], deg_out) and torch.equal(iptr[1:] - iptr[:-1], deg_in)
+
+
+def test_edge_layout_rejects_self_loops():
+    from mpntrackseg_b200 import ops
+    ei = torch.tensor([[0, 1, 2], [1, 1, 0]], device=dev())
+    with pytest.raises(ValueError, match='self-loops'):
+        ops.edge_layout(ei, 3)
+
+
+# ------------------------------------------------------------------ model
+@pytest.mark.parametrize('name', list(CASES))
+def test_forward_matches_reference_golden(name):
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    model = make_model(c['mp'], c['P'])
+    data = Data()
+    data.x = win.x.to(dev())
+    data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    data.edge_attr = torch.from_numpy(gold['edge_attr']).to(dev())
+    with torch.no_grad():
+        out = model(data, return_state=True)
+    assert len(out['classified_edges']) == gold['logits'].shape[0]
+    assert all(tuple(t.shape) == (gold['edge_index'].shape[1], 1) for t in out['classified_edges'])
+    logits = torch.stack([t.view(-1) for t in out['classified_edges']]).cpu().numpy()
+    assert_logits_close(logits, gold['logits'], name)
+    scale = max(1.0, float(np.abs(gold['node_state']).max()))
+    np.testing.assert_allclose(out['node_state'].cpu().numpy(), gold['node_state'], atol=2e-4 * scale, rtol=1e-3)
+    lay = out['layout']
+    e_state = torch.empty_like(out['edge_state_slots'])
+    e_state[lay.slot_edge[:lay.num_edges].long()] = out['edge_state_slots']
+    scale = max(1.0, float(np.abs(gold['edge_state']).max()))
+    np.testing.assert_allclose(e_state.cpu().numpy(), gold['edge_state'], atol=2e-4 * scale, rtol=1e-3)
+
+
+def test_forward_is_deterministic_and_order_invariant():
+    """No float atomics: two runs are bit-identical; permuting the caller's edge order
+    permutes the logits and nothing else."""
+    c = load_case('config1')
+    win, gold = c['win'], c['gold']
+    model = make_model(c['mp'], c['P'])
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    ea = torch.from_numpy(gold['edge_attr']).to(dev())
+    data = Data()
+    data.x, data.edge_index, data.edge_attr = win.x.to(dev()), ei, ea
+    with torch.no_grad():
+        a = model(data)['classified_edges'][-1]
+        b = model(data)['classified_edges'][-1]
+    assert torch.equal(a, b)
+    e = ei.shape[1]
+    half = e // 2
+    # swap the two halves: still (row<col) group + (row>col) group, each internally stable
+    perm = torch.cat((torch.arange(half, e), torch.arange(0, half))).to(dev())
+    data.edge_index, data.edge_attr = ei[:, perm], ea[perm]
+    with torch.no_grad():
+        p = model(data)['classified_edges'][-1]
+    assert torch.equal(p, a[perm])
+
+
+def test_metalayer_single_step_matches_oracle():
+    c = load_case('kitti_shape')
+    win, gold, P = c['win'], c['gold'], c['P']
+    model = make_model(c['mp'], P)
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(win.N, 64, generator=g).abs()
+    ea = torch.randn(ei.shape[1], 32, generator=g).abs()
+    with torch.no_grad():
+        e_ref = mpn_ref.edge_update(P, x, ei, ea)
+        x_ref = mpn_ref.node_update(P, x, ei, e_ref)
+        x_new, e_new = model.MPNet(x.to(dev()), ei.to(dev()), ea.to(dev()))
+    np.testing.assert_allclose(e_new.cpu().numpy(), e_ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(x_new.cpu().numpy(), x_ref.numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_isolated_nodes_and_empty_graph():
+    """Nodes without in- or out-edges aggregate to zero (scatter_add zero fill); E = 0 works."""
+    mp = default_graph_model_params(3, 2)
+    P = synth.make_params(mp, seed=2, gain=1.5, core_only=True)
+    model = make_model(mp, P)
+    g = torch.Generator().manual_seed(1)
+    n = 9
+    x = torch.randn(n, 2048, generator=g).abs()
+    pairs = torch.tensor([[0, 0, 2], [2, 5, 5]])                       # nodes 1,3,4,6,7,8 isolated
+    ei = torch.cat((pairs, pairs.flip(0)), dim=1)
+    ea = torch.randn(3, 6, generator=g).repeat(2, 1)
+    for edge_index, edge_attr in ((ei, ea), (ei[:, :0], ea[:0])):
+        data = Data()
+        data.x, data.edge_index, data.edge_attr = x.to(dev()), edge_index.to(dev()), edge_attr.to(dev())
+        with torch.no_grad():
+            out = model(data, return_state=True)
+            ref = mpn_ref.mpn_forward(P, mp, x, edge_index, edge_attr, return_state=True)
+        assert len(out['classified_edges']) == 2
+        for a, b in zip(out['classified_edges'], ref['classified_edges']):
+            assert tuple(a.shape) == tuple(b.shape)
+            if b.numel():
+                assert_logits_close(a.cpu().numpy(), b.numpy(), 'isolated')
+        np.testing.assert_allclose(out['node_state'].cpu().numpy(), ref['node_state'].numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_config2_scale_against_oracle():
+    """MOTS20-scale window (BASELINE config 2: 15 frames x 150 detections, k=50): full hot
+    path on the GPU (graph build + forward) against the oracle on the same inputs."""
+    from mpntrackseg_b200.data.mot_graph import MOTGraph
+    win = synth.make_window(T=15, D=150, k=50, seed=4, node_feats='pooled')
+    ds = default_dataset_params(top_k_nns=50, frames_per_graph=15)
+    mp = default_graph_model_params(12, 11)
+    P = synth.make_params(mp, seed=9, gain=1.25, core_only=True)
+    ref_g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds)
+    with torch.no_grad():
+        ref = mpn_ref.mpn_forward(P, mp, win.x, ref_g['edge_index'], ref_g['edge_attr'])
+    g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
+    assert torch.equal(g.edge_index.cpu(), ref_g['edge_index'])
+    model = make_model(mp, P)
+    with torch.no_grad():
+        out = model(g)
+    got = torch.stack([t.view(-1) for t in out['classified_edges']]).cpu().numpy()
+    exp = torch.stack([t.view(-1) for t in ref['classified_edges']]).numpy()
+    assert_logits_close(got, exp, 'config2')
+
+
+def test_encoders_against_torch():
+    from mpntrackseg_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 2048, 8, 4, generator=g)
+    np.testing.assert_allclose(ops.avgpool(x.to(dev())).cpu().numpy(), x.mean(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-6)
+    x2 = torch.randn(5, 7, 3, 3, generator=g)                          # odd spatial size -> scalar path
+    np.testing.assert_allclose(ops.avgpool(x2.to(dev())).cpu().numpy(), x2.mean(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-6)
+    a, w, b = torch.randn(130, 2048, generator=g), torch.randn(128, 2048, generator=g) / 45, torch.randn(128, generator=g)
+    ref = torch.relu(torch.nn.functional.linear(a, w, b))
+    np.testing.assert_allclose(ops.linear(a.to(dev()), w.to(dev()), b.to(dev()), True).cpu().numpy(), ref.numpy(),
+                               rtol=1e-4, atol=1e-4)
+    a, w = torch.randn(3, 5, generator=g), torch.randn(1, 5, generator=g)
+    np.testing.assert_allclose(ops.linear(a.to(dev()), w.to(dev()), None, False).cpu().numpy(),
+                               torch.nn.functional.linear(a, w).numpy(), rtol=1e-5, atol=1e-6)
