@@ -246,7 +246,7 @@ def run_b200(a):
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host buffers in, logits out, copies inside the timed region
-    for _ in range(max(1, a.warmup // 2)):
+    for _ in range(max(2, a.warmup)):
         step_e2e()
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)

@@ -51,7 +51,7 @@ def knn_keep_mask(pwise_dist, edge_ixs, num_nodes, top_k_nns, reciprocal_k_nns=F
     dense[r, c] = pwise_dist.view(-1).float()
     if not symmetric_edges:
         dense[c, r] = pwise_dist.view(-1).float()
-    order = torch.argsort(dense, dim=1, descending=False)          # graph.py:65
+    order = torch.argsort(dense, dim=1, descending=False, stable=True)   # graph.py:65 (+ stable)
     rank = torch.empty_like(order)
     rank.scatter_(1, order, torch.arange(n).expand(n, n).contiguous())  # graph.py:69-70
     near = rank < int(top_k_nns)
