@@ -190,6 +190,18 @@ int mpn_mp_forward(const mpn_core_weights* h_w, const mpn_edge_layout* h_g,
                    int32_t first_class_step, void* workspace, float* logits,
                    float* x_out, float* e_out, void* stream);
 
+/* Same contract as mpn_mp_forward (num_steps >= 1), evaluated on the tcgen05 tensor cores:
+ * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).
+ * *status (device int32) is set non-zero if any activation left the fp16 range (> 65504); the
+ * outputs are then invalid and the caller must rerun with mpn_mp_forward (fp32 kernels).
+ * workspace bytes: mpn_mp_tc_workspace(N, E). */
+int64_t mpn_mp_tc_workspace(int64_t num_nodes, int64_t num_edges);
+int mpn_mp_forward_tc(const mpn_core_weights* h_w, const mpn_edge_layout* h_g, const float* x_init,
+                      const float* e_init, int32_t num_steps, int32_t first_class_step,
+                      void* workspace, float* logits, float* x_out, float* e_out, int32_t* status,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,702 @@
+// Fused message-passing step on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// One 128-edge tile = one M=128 MMA tile: TMEM lane i <-> edge slot i <-> epilogue thread i.
+// The four dense layers of a step (edge MLP 160->80->16, flow MLP 80->56->32) run as
+// tcgen05.mma kind::f16 with the ACTIVATIONS in TMEM (A operand, written by the epilogue
+// threads with tcgen05.st) and the WEIGHTS resident in shared memory (B operand, K-major).
+// Precision: every operand is split v ~= hi + lo in fp16 (22 significant bits) and each K step
+// issues hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM -- single-pass bf16/tf32 breaks
+// the 1e-3 parity bar after 12 recurrent steps, bf16 hi/lo is 10-20x less accurate than fp16
+// hi/lo (tools/emulate_split_bf16.py).  fp16 range overflow (> 65504) is detected and reported
+// through `status`; the caller then reruns on the fp32 kernels (mp_step.cu).
+//
+//   x[row] part of edge layer 0 is hoisted: prow[r] = W0[:, 0:64] [x_init[r] | x_lat[r]] + b0
+//   (fp32, computed by the node kernel), added in the first epilogue.
+//
+// State lives in HBM already split: per node 128 B = [hi(32 halfs) | lo(32 halfs)], per edge
+// 64 B = [hi(16) | lo(16)], so loads are plain copies into TMEM and the bytes per edge-update
+// stay at 200.
+//
+// Warp roles (288 threads, 1 CTA / SM): warps 0-3 = epilogue group 0, warps 4-7 = group 1 (two
+// tiles in flight, each owns 256 of the 512 TMEM columns), warp 8 = TMEM allocator + the single
+// MMA-issuing thread.  While one group runs an epilogue the tensor core runs the other's layer.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mpn {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int TS = 128;
+constexpr int DN = 32, DE = 16, EH = 80, FH = 56, FHP = 64, CH = 8;
+constexpr int NTHREADS = 288;
+
+// ---- shared-memory weight image (bytes). Slab = one K=16 step of a B operand: [n/8][k/8][n%8][8 halfs]
+constexpr int L1_KS = 6, L1_SLAB = EH * 32;
+constexpr int L2_KS = 5, L2_SLAB = DE * 32;
+constexpr int L3_KS = 5, L3_SLAB = FHP * 32;
+constexpr int L4_KS = 4, L4_SLAB = DN * 32;
+constexpr int OFF_L1H = 0, OFF_L1L = OFF_L1H + L1_KS * L1_SLAB;
+constexpr int OFF_L2H = OFF_L1L + L1_KS * L1_SLAB, OFF_L2L = OFF_L2H + L2_KS * L2_SLAB;
+constexpr int OFF_L3H = OFF_L2L + L2_KS * L2_SLAB, OFF_L3L = OFF_L3H + L3_KS * L3_SLAB;
+constexpr int OFF_L4H = OFF_L3L + L3_KS * L3_SLAB, OFF_L4L = OFF_L4H + L4_KS * L4_SLAB;
+constexpr int OFF_F32 = OFF_L4L + L4_KS * L4_SLAB;          // fp32 tail
+constexpr int F_B1 = 0, F_FB0 = F_B1 + DE, F_FB1 = F_FB0 + FHP, F_CW0 = F_FB1 + DN, F_CB0 = F_CW0 + DE * CH,
+              F_CW1 = F_CB0 + CH, F_CB1 = F_CW1 + CH, F_COUNT = F_CB1 + 4;
+constexpr int IMG_BYTES = (OFF_F32 + F_COUNT * 4 + 127) / 128 * 128;
+
+// ---- TMEM column map inside a group's 256 columns
+constexpr int C_XCH = 0, C_XCL = 32;        // x[col] hi / lo            (K = 64)
+constexpr int C_EH = 64, C_EL = 80;         // [e_init | e] hi / lo      (K = 32)
+constexpr int C_D1 = 96;                    // layer-1 accumulator, 80 cols
+constexpr int C_A2H = 176, C_A2L = 216;     // layer-2 input hi / lo     (K = 80)
+constexpr int C_D2 = 64;                    // layer-2 accumulator, 16 cols (over the dead E region)
+constexpr int C_A3H = 80, C_A3L = 88;       // e' hi / lo                (K = 16)
+constexpr int C_D3 = 96;                    // layer-3 accumulator, 64 cols
+constexpr int C_A4H = 176, C_A4L = 208;     // layer-4 input hi / lo     (K = 64)
+constexpr int C_D4 = 0;                     // layer-4 accumulator, 32 cols (over the dead x[col])
+
+// ---- dynamic shared memory map
+constexpr int MSG_LD = DN + 1;
+constexpr int SM_MSG = IMG_BYTES;                                   // float [2][TS*MSG_LD]
+constexpr int SM_ROWS = SM_MSG + 2 * TS * MSG_LD * 4;               // int   [2][TS+4]
+constexpr int SM_BAR = SM_ROWS + 2 * (TS + 4) * 4;                  // u64 a_ready[2], d_ready[2]
+constexpr int SM_TMEM = SM_BAR + 4 * 8;
+constexpr int SMEM_BYTES = SM_TMEM + 16;
+
+__device__ __forceinline__ int slab_off(int n, int k16) {           // byte offset inside a slab
+  return (n >> 3) * 256 + (k16 >> 3) * 128 + (n & 7) * 16 + (k16 & 7) * 2;
+}
+
+// =================================================================== weight packing (once per forward)
+// One image per direction (flow_out / flow_in); layers 1-2 and the classifier are shared.
+__global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ img_out, uint8_t* __restrict__ img_in) {
+  for (int dir = 0; dir < 2; ++dir) {
+    uint8_t* img = dir == 0 ? img_out : img_in;
+    const float* f0 = dir == 0 ? w.fout_w0 : w.fin_w0;
+    const float* f1 = dir == 0 ? w.fout_w1 : w.fin_w1;
+    const float* fb0 = dir == 0 ? w.fout_b0 : w.fin_b0;
+    const float* fb1 = dir == 0 ? w.fout_b1 : w.fin_b1;
+    auto put = [&](int off_h, int off_l, int slab_bytes, int n, int k, float v) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      const int o = (k >> 4) * slab_bytes + slab_off(n, k & 15);
+      *reinterpret_cast<__half*>(img + off_h + o) = h;
+      *reinterpret_cast<__half*>(img + off_l + o) = l;
+    };
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < EH * 96; i += nt) {            // edge layer 0, input columns 64..159
+      const int n = i / 96, k = i % 96;
+      put(OFF_L1H, OFF_L1L, L1_SLAB, n, k, w.edge_w0[n * 160 + 64 + k]);
+    }
+    for (int i = tid; i < DE * EH; i += nt) {            // edge layer 1
+      const int n = i / EH, k = i % EH;
+      put(OFF_L2H, OFF_L2L, L2_SLAB, n, k, w.edge_w1[n * EH + k]);
+    }
+    for (int i = tid; i < FHP * 80; i += nt) {           // flow layer 0 (rows padded 56 -> 64)
+      const int n = i / 80, k = i % 80;
+      put(OFF_L3H, OFF_L3L, L3_SLAB, n, k, n < FH ? f0[n * 80 + k] : 0.f);
+    }
+    for (int i = tid; i < DN * FHP; i += nt) {           // flow layer 1 (K padded 56 -> 64)
+      const int n = i / FHP, k = i % FHP;
+      put(OFF_L4H, OFF_L4L, L4_SLAB, n, k, k < FH ? f1[n * FH + k] : 0.f);
+    }
+    float* ft = reinterpret_cast<float*>(img + OFF_F32);
+    for (int i = tid; i < F_COUNT; i += nt) {
+      float v = 0.f;
+      if (i < F_FB0) v = w.edge_b1[i - F_B1];
+      else if (i < F_FB1) v = (i - F_FB0) < FH ? fb0[i - F_FB0] : 0.f;
+      else if (i < F_CW0) v = fb1[i - F_FB1];
+      else if (i < F_CB0) { const int q = i - F_CW0, in = q / CH, o = q % CH; v = w.cls_w0[o * DE + in]; }
+      else if (i < F_CW1) v = w.cls_b0[i - F_CB0];
+      else if (i < F_CB1) v = w.cls_w1[i - F_CW1];
+      else if (i == F_CB1) v = w.cls_b1[0];
+      ft[i] = v;
+    }
+  }
+}
+
+// =================================================================== node-side kernels
+__device__ __forceinline__ void store_split_row(__half* __restrict__ row64, int lane, float v, int* ovf) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  row64[lane] = h;
+  row64[32 + lane] = l;
+  if (!(fabsf(v) < 65000.f)) *ovf = 1;
+}
+
+// Once per forward: split x_init, and the hoisted row terms
+//   pinit[r] = W0[:, 0:32] x_init[r] + b0 ; prow[r] = pinit[r] + W0[:, 32:64] x_init[r]  (x_lat = x_init before step 1)
+__global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict__ x_init, int64_t n,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0,
+                                                         __half* __restrict__ xi, __half* __restrict__ xl0,
+                                                         float* __restrict__ pinit, float* __restrict__ prow,
+                                                         int32_t* __restrict__ status) {
+  __shared__ float s_w[64 * EH];     // [i][o], i over W0 columns 0..63
+  __shared__ float s_b[EH];
+  for (int idx = threadIdx.x; idx < 64 * EH; idx += blockDim.x) {
+    const int i = idx / EH, o = idx % EH;
+    s_w[idx] = w0[o * 160 + i];
+  }
+  for (int o = threadIdx.x; o < EH; o += blockDim.x) s_b[o] = b0[o];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int ovf = 0;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float v = x_init[r * DN + lane];
+    store_split_row(xi + r * 64, lane, v, &ovf);
+    store_split_row(xl0 + r * 64, lane, v, &ovf);
+    float a0[3], a1[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int o = lane + 32 * q; a0[q] = o < EH ? s_b[o] : 0.f; a1[q] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < DN; ++i) {
+      const float xv = __shfl_sync(0xffffffffu, v, i);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int o = lane + 32 * q;
+        if (o < EH) { a0[q] = fmaf(xv, s_w[i * EH + o], a0[q]); a1[q] = fmaf(xv, s_w[(32 + i) * EH + o], a1[q]); }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int o = lane + 32 * q;
+      if (o < EH) { pinit[r * EH + o] = a0[q]; prow[r * EH + o] = a0[q] + a1[q]; }
+    }
+  }
+  if (ovf) atomicOr(status, 1);
+}
+
+// Per step: x' = ReLU(Wn [flow_in | flow_out] + bn)  (models/mpn.py:97-99), then the split copy of
+// x' for the next step's gathers and prow[r] = pinit[r] + W0[:, 32:64] x'.
+__global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
+                                                      int64_t num_nodes, int64_t num_out, int32_t tiles_out,
+                                                      const float* __restrict__ flow, const float* __restrict__ part,
+                                                      const float* __restrict__ node_w, const float* __restrict__ node_b,
+                                                      const float* __restrict__ w0, const float* __restrict__ pinit,
+                                                      __half* __restrict__ xl_next, float* __restrict__ prow,
+                                                      float* __restrict__ x_out, int32_t* __restrict__ status) {
+  __shared__ float s_wn[2 * DN * DN];   // [in][out]
+  __shared__ float s_bn[DN];
+  __shared__ float s_w0[DN * EH];       // [i][o] over W0 columns 32..63
+  for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
+    const int i = idx / DN, o = idx - i * DN;
+    s_wn[idx] = node_w[o * 2 * DN + i];
+  }
+  for (int o = threadIdx.x; o < DN; o += blockDim.x) s_bn[o] = node_b[o];
+  for (int idx = threadIdx.x; idx < DN * EH; idx += blockDim.x) {
+    const int i = idx / EH, o = idx % EH;
+    s_w0[idx] = w0[o * 160 + 32 + i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int ovf = 0;
+  for (int64_t r = warp; r < num_nodes; r += nwarps) {
+    float fl[2];                       // fl[0] = flow_in[lane], fl[1] = flow_out[lane]
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int32_t* ptr = d == 0 ? in_ptr : out_ptr;
+      const int64_t seg_base = d == 0 ? num_out : 0;
+      const int tile_off = d == 0 ? tiles_out : 0;
+      const int64_t s0 = ptr[r], s1 = ptr[r + 1];
+      float v = 0.f;
+      if (s1 > s0) {
+        const int64_t ta = (s0 - seg_base) / TS, tb = (s1 - 1 - seg_base) / TS;
+        if (ta == tb) {
+          v = flow[r * 2 * DN + d * DN + lane];
+        } else {
+          const bool first_in_tile = (s0 - seg_base) % TS == 0;
+          v = part[((tile_off + ta) * 2 + (first_in_tile ? 0 : 1)) * DN + lane];
+          for (int64_t t = ta + 1; t <= tb; ++t) v += part[((tile_off + t) * 2) * DN + lane];
+        }
+      }
+      fl[d] = v;
+    }
+    float acc = s_bn[lane];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int i = 0; i < DN; ++i) acc = fmaf(__shfl_sync(0xffffffffu, fl[d], i), s_wn[(d * DN + i) * DN + lane], acc);
+    const float xn = fmaxf(acc, 0.f);
+    if (x_out != nullptr) x_out[r * DN + lane] = xn;
+    store_split_row(xl_next + r * 64, lane, xn, &ovf);
+    float a[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int o = lane + 32 * q; a[q] = o < EH ? pinit[r * EH + o] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < DN; ++i) {
+      const float xv = __shfl_sync(0xffffffffu, xn, i);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int o = lane + 32 * q;
+        if (o < EH) a[q] = fmaf(xv, s_w0[i * EH + o], a[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int o = lane + 32 * q;
+      if (o < EH) prow[r * EH + o] = a[q];
+    }
+  }
+  if (ovf) atomicOr(status, 1);
+}
+
+// e (fp32 [E,16], slot order) -> split rows [hi(16) | lo(16)] halfs
+__global__ void split_edges_kernel(const float* __restrict__ e, int64_t num_edges, uint4* __restrict__ out,
+                                   int32_t* __restrict__ status) {
+  int ovf = 0;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_edges; s += (int64_t)gridDim.x * blockDim.x) {
+    const float4* p = reinterpret_cast<const float4*>(e + s * DE);
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = __ldg(p + q);
+      split2(v.x, v.y, hi[2 * q], lo[2 * q]);
+      split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+      if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) < 65000.f)) ovf = 1;
+    }
+    out[s * 4 + 0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out[s * 4 + 1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    out[s * 4 + 2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    out[s * 4 + 3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  if (ovf) atomicOr(status, 1);
+}
+
+// split rows -> fp32 (final edge state for callers that ask for it)
+__global__ void unsplit_edges_kernel(const uint4* __restrict__ in, int64_t num_edges, float* __restrict__ e) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_edges; s += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 h0 = in[s * 4], h1 = in[s * 4 + 1], l0 = in[s * 4 + 2], l1 = in[s * 4 + 3];
+    const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+      e[s * DE + 2 * j] = a.x + b.x;
+      e[s * DE + 2 * j + 1] = a.y + b.y;
+    }
+  }
+}
+
+// =================================================================== the edge kernel
+struct TcArgs {
+  const int32_t* slot_row; const int32_t* slot_col; const int32_t* slot_edge;
+  int64_t num_edges, num_out;
+  int32_t tiles_out, tiles_in;
+  const uint4* xi;       // [N][8]  x_init split rows (128 B)
+  const uint4* xl;       // [N][8]  x_lat split rows
+  const float* prow;     // [N][80] hoisted row term (incl. bias)
+  const uint4* ei;       // [E][4]  e_init split rows (64 B)
+  const uint4* es_in;    // [E][4]  e split rows
+  uint4* es_out;         // may alias es_in
+  float* flow; float* part; float* logits;
+  const uint8_t* wimg_out; const uint8_t* wimg_in;
+  int32_t* status;
+};
+
+// relu(acc + add) for 16 values, split to fp16 hi/lo words; accumulates the overflow detector
+__device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const float (&add)[16], uint32_t (&hi)[8],
+                                             uint32_t (&lo)[8], uint32_t& ovf) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = fmaxf(__uint_as_float(acc[2 * j]) + add[2 * j], 0.f);
+    const float b = fmaxf(__uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], 0.f);
+    split2(a, b, hi[j], lo[j]);
+    ovf |= hi[j] + 0x04000400u;        // fp16 inf (0x7C00) + 0x0400 sets the half's top bit
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // CTAs [0, n_out_ctas) walk flow_out tiles, the rest walk flow_in tiles.
+  const int total_tiles = a.tiles_out + a.tiles_in;
+  int n_out_ctas = (int)(((int64_t)gridDim.x * a.tiles_out + total_tiles - 1) / total_tiles);
+  if (a.tiles_out > 0 && n_out_ctas == 0) n_out_ctas = 1;
+  if (a.tiles_in > 0 && n_out_ctas >= (int)gridDim.x) n_out_ctas = gridDim.x - 1;
+  if (a.tiles_in == 0) n_out_ctas = gridDim.x;
+  const bool dir_out = (int)blockIdx.x < n_out_ctas;
+  const int cta_in_dir = dir_out ? blockIdx.x : blockIdx.x - n_out_ctas;
+  const int ctas_in_dir = dir_out ? n_out_ctas : gridDim.x - n_out_ctas;
+  const int tiles_dir = dir_out ? a.tiles_out : a.tiles_in;
+  const int64_t seg_base = dir_out ? 0 : a.num_out;
+  const int64_t seg_end = dir_out ? a.num_out : a.num_edges;
+  const int tile_off = dir_out ? 0 : a.tiles_out;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);     // a_ready[0..1], d_ready[2..3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], TS); mbar_init(&bars[1], TS);
+    mbar_init(&bars[2], 1);  mbar_init(&bars[3], 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  const float* s_f = reinterpret_cast<const float*>(smem + OFF_F32);
+
+  if (warp < 8) {
+    // ================================================================ epilogue groups
+    const int g = warp >> 2;
+    const int gt = tid & (TS - 1);
+    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;
+    float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + g * TS * MSG_LD;
+    int32_t* s_rows = reinterpret_cast<int32_t*>(smem + SM_ROWS) + g * (TS + 4);
+    uint64_t* a_ready = &bars[g];
+    uint64_t* d_ready = &bars[2 + g];
+    uint32_t pd = 0;
+    uint32_t ovf = 0;
+    for (int p = cta_in_dir; 2 * p + g < tiles_dir; p += ctas_in_dir) {
+      const int t = 2 * p + g;
+      const int64_t base = seg_base + (int64_t)t * TS;
+      const int cnt = (int)(seg_end - base < TS ? seg_end - base : TS);
+      const bool valid = gt < cnt;
+      const int64_t slot = valid ? base + gt : base + cnt - 1;       // clamp: loads stay in range
+      const int32_t r = a.slot_row[slot], c = a.slot_col[slot];
+      s_rows[1 + gt] = valid ? r : -1;
+      if (gt == 0) {
+        s_rows[0] = base > seg_base ? a.slot_row[base - 1] : -1;
+        s_rows[TS + 1] = base + cnt < seg_end ? a.slot_row[base + cnt] : -1;
+      }
+      // ---- operands of layer 1 (and the x[col] part of layer 3): global -> registers -> TMEM
+      {
+        const uint4* pxi = a.xi + (int64_t)c * 8;
+        const uint4* pxl = a.xl + (int64_t)c * 8;
+        const uint4* pei = a.ei + slot * 4;
+        const uint4* pes = a.es_in + slot * 4;
+        uint4 q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = __ldg(pxi + j);
+        uint4 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = __ldg(pxl + j);
+        uint4 ev[4], es[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ev[j] = __ldg(pei + j); es[j] = pes[j]; }
+        auto st2 = [&](int col, const uint4& x, const uint4& y) {
+          const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+          tmem_st8(tlane + col, w8);
+        };
+        st2(C_XCH + 0, q[0], q[1]);  st2(C_XCH + 8, q[2], q[3]);     // x_init hi
+        st2(C_XCL + 0, q[4], q[5]);  st2(C_XCL + 8, q[6], q[7]);     // x_init lo
+        st2(C_XCH + 16, u[0], u[1]); st2(C_XCH + 24, u[2], u[3]);    // x_lat hi
+        st2(C_XCL + 16, u[4], u[5]); st2(C_XCL + 24, u[6], u[7]);    // x_lat lo
+        st2(C_EH + 0, ev[0], ev[1]); st2(C_EL + 0, ev[2], ev[3]);    // e_init hi / lo
+        st2(C_EH + 8, es[0], es[1]); st2(C_EL + 8, es[2], es[3]);    // e hi / lo
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+
+      // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand
+      {
+        const float4* pr = reinterpret_cast<const float4*>(a.prow + (int64_t)r * EH);
+        mbar_wait(d_ready, pd); pd ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < EH / 16; ++ch) {
+          uint32_t acc[16];
+          tmem_ld16(tlane + C_D1 + 16 * ch, acc);
+          float add[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldg(pr + 4 * ch + j);
+            add[4 * j] = v.x; add[4 * j + 1] = v.y; add[4 * j + 2] = v.z; add[4 * j + 3] = v.w;
+          }
+          tc_wait_ld();
+          uint32_t hi[8], lo[8];
+          relu_split16(acc, add, hi, lo, ovf);
+          tmem_st8(tlane + C_A2H + 8 * ch, hi);
+          tmem_st8(tlane + C_A2L + 8 * ch, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      }
+      // ---- epilogue 2: e' = ReLU(D2 + b1) -> state, layer-3 operand, classifier
+      {
+        mbar_wait(d_ready, pd); pd ^= 1;
+        tc_fence_after();
+        uint32_t acc[16];
+        tmem_ld16(tlane + C_D2, acc);
+        float add[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) add[j] = s_f[F_B1 + j];
+        tc_wait_ld();
+        uint32_t hi[8], lo[8];
+        relu_split16(acc, add, hi, lo, ovf);
+        tmem_st8(tlane + C_A3H, hi);
+        tmem_st8(tlane + C_A3L, lo);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+        if (valid) {
+          uint4* dst = a.es_out + (base + gt) * 4;
+          dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          if (a.logits != nullptr) {                                  // classifier 16 -> 8 -> 1 (fp32)
+            float hc[CH];
+#pragma unroll
+            for (int o = 0; o < CH; ++o) hc[o] = s_f[F_CB0 + o];
+#pragma unroll
+            for (int i = 0; i < DE; ++i) {
+              const float ei = fmaxf(__uint_as_float(acc[i]) + add[i], 0.f);
+#pragma unroll
+              for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, s_f[F_CW0 + i * CH + o], hc[o]);
+            }
+            float lg = s_f[F_CB1];
+#pragma unroll
+            for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), s_f[F_CW1 + o], lg);
+            a.logits[a.slot_edge[base + gt]] = lg;
+          }
+        }
+      }
+      // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand
+      {
+        mbar_wait(d_ready, pd); pd ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < FHP / 16; ++ch) {
+          uint32_t acc[16];
+          tmem_ld16(tlane + C_D3 + 16 * ch, acc);
+          float add[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) add[j] = s_f[F_FB0 + 16 * ch + j];
+          tc_wait_ld();
+          uint32_t hi[8], lo[8];
+          relu_split16(acc, add, hi, lo, ovf);
+          tmem_st8(tlane + C_A4H + 8 * ch, hi);
+          tmem_st8(tlane + C_A4L + 8 * ch, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      }
+      // ---- epilogue 4: m = ReLU(D4 + fb1), per-row sums in slot order
+      {
+        mbar_wait(d_ready, pd); pd ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < DN / 16; ++ch) {
+          uint32_t acc[16];
+          tmem_ld16(tlane + C_D4 + 16 * ch, acc);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float m = fmaxf(__uint_as_float(acc[j]) + s_f[F_FB1 + 16 * ch + j], 0.f);
+            s_msg[gt * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
+          }
+        }
+        tc_fence_before();
+        named_barrier(1 + g, TS);
+        if ((warp & 3) == 0) {
+          const int f = lane;
+          const int dir_off = dir_out ? DN : 0;                       // cat(flow_in, flow_out), mpn.py:97
+          const int tile_id = tile_off + t;
+          int seg_first_t = 0;
+          int32_t cur = s_rows[1];
+          float sum = 0.f;
+          for (int q = 0; q <= cnt; ++q) {
+            const int32_t rq = q < cnt ? s_rows[1 + q] : -2;
+            if (rq != cur) {
+              const bool starts_before = seg_first_t == 0 && s_rows[0] == cur;
+              const bool continues = q == cnt && s_rows[TS + 1] == cur;
+              if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
+              else a.part[((int64_t)tile_id * 2 + (seg_first_t == 0 ? 0 : 1)) * DN + f] = sum;
+              cur = rq; sum = 0.f; seg_first_t = q;
+            }
+            if (q < cnt) sum += s_msg[q * MSG_LD + f];
+          }
+        }
+        named_barrier(1 + g, TS);
+      }
+    }
+    if (ovf & 0x80008000u) atomicOr(a.status, 1);
+  } else if (lane == 0) {
+    // ================================================================ MMA issuer (one thread)
+    const uint32_t img = smem_u32(smem);
+    uint32_t pa[2] = {0, 0};
+    const uint32_t id80 = idesc_f16(128, EH), id16 = idesc_f16(128, DE), id64 = idesc_f16(128, FHP),
+                   id32 = idesc_f16(128, DN);
+    auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, bool first) {
+      const uint64_t dh = smem_desc_kmajor(bh, 128, 256), dl = smem_desc_kmajor(bl, 128, 256);
+      mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
+      mma_ts(d, ah, dl, idesc, 1u);
+      mma_ts(d, al, dh, idesc, 1u);
+    };
+    for (int p = cta_in_dir; 2 * p < tiles_dir; p += ctas_in_dir) {
+      for (int layer = 1; layer <= 4; ++layer) {
+        for (int g = 0; g < 2; ++g) {
+          if (2 * p + g >= tiles_dir) continue;
+          const uint32_t cb = tbase + (uint32_t)g * 256u;
+          mbar_wait(&bars[g], pa[g]); pa[g] ^= 1;
+          tc_fence_after();
+          if (layer == 1) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              step3(cb + C_D1, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, img + OFF_L1H + ks * L1_SLAB,
+                    img + OFF_L1L + ks * L1_SLAB, id80, ks == 0);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              step3(cb + C_D1, cb + C_EH + 8 * ks, cb + C_EL + 8 * ks, img + OFF_L1H + (4 + ks) * L1_SLAB,
+                    img + OFF_L1L + (4 + ks) * L1_SLAB, id80, false);
+          } else if (layer == 2) {
+#pragma unroll
+            for (int ks = 0; ks < L2_KS; ++ks)
+              step3(cb + C_D2, cb + C_A2H + 8 * ks, cb + C_A2L + 8 * ks, img + OFF_L2H + ks * L2_SLAB,
+                    img + OFF_L2L + ks * L2_SLAB, id16, ks == 0);
+          } else if (layer == 3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              step3(cb + C_D3, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, img + OFF_L3H + ks * L3_SLAB,
+                    img + OFF_L3L + ks * L3_SLAB, id64, ks == 0);
+            step3(cb + C_D3, cb + C_A3H, cb + C_A3L, img + OFF_L3H + 4 * L3_SLAB, img + OFF_L3L + 4 * L3_SLAB, id64, false);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < L4_KS; ++ks)
+              step3(cb + C_D4, cb + C_A4H + 8 * ks, cb + C_A4L + 8 * ks, img + OFF_L4H + ks * L4_SLAB,
+                    img + OFF_L4L + ks * L4_SLAB, id32, ks == 0);
+          }
+          mma_commit(&bars[2 + g]);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tbase);
+}
+
+struct TcWorkspace {
+  __half* xi; __half* xl[2];
+  float* pinit; float* prow;
+  uint4* ei; uint4* es;
+  float* flow; float* part;
+  uint8_t* wimg_out; uint8_t* wimg_in;
+};
+
+static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
+  Carver cv(ws);
+  const int64_t tiles = ceil_div(e, TS) + 2;
+  TcWorkspace w;
+  w.xi = cv.take<__half>(n * 64);
+  w.xl[0] = cv.take<__half>(n * 64);
+  w.xl[1] = cv.take<__half>(n * 64);
+  w.pinit = cv.take<float>(n * EH);
+  w.prow = cv.take<float>(n * EH);
+  w.ei = cv.take<uint4>(e * 4);
+  w.es = cv.take<uint4>(e * 4);
+  w.flow = cv.take<float>(n * 2 * DN);
+  w.part = cv.take<float>(tiles * 2 * DN);
+  w.wimg_out = cv.take<uint8_t>(IMG_BYTES);
+  w.wimg_in = cv.take<uint8_t>(IMG_BYTES);
+  if (out) *out = w;
+  return cv.off;
+}
+
+}  // namespace tc
+}  // namespace mpn
+
+using namespace mpn;
+
+extern "C" {
+
+int64_t mpn_mp_tc_workspace(int64_t n, int64_t e) {
+  return tc::carve(nullptr, n > 0 ? n : 1, e > 0 ? e : 1, nullptr) + 256;
+}
+
+int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const float* x_init, const float* e_init,
+                      int32_t num_steps, int32_t first_class_step, void* ws, float* logits, float* x_out,
+                      float* e_out, int32_t* status, void* stream) {
+  MPN_CHECK_ARG(w && g, "mp_forward_tc: null descriptor");
+  MPN_CHECK_ARG(w->dn == 32 && w->de == 16 && w->edge_h == 80 && w->flow_h == 56 && w->cls_h == 8,
+                "mp_forward_tc: built for widths dn=32 de=16 edge_h=80 flow_h=56 cls_h=8 (got %d %d %d %d %d)", w->dn,
+                w->de, w->edge_h, w->flow_h, w->cls_h);
+  MPN_CHECK_ARG(num_steps >= 1, "mp_forward_tc: num_steps must be >= 1 (use mpn_mp_forward for 0)");
+  MPN_CHECK_ARG(ws && status, "mp_forward_tc: null workspace / status");
+  const int64_t n = g->num_nodes, e = g->num_edges;
+  cudaStream_t s = as_stream(stream);
+  MPN_CUDA(cudaMemsetAsync(status, 0, 4, s));
+  if (n == 0) return MPN_OK;
+  tc::TcWorkspace m;
+  tc::carve(ws, n, e > 0 ? e : 1, &m);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in); count_launch();
+  const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 8);
+  tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, status);
+  count_launch();
+  if (e > 0) {
+    const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div(e, 256), (int64_t)sms * 8);
+    tc::split_edges_kernel<<<egrid, 256, 0, s>>>(e_init, e, m.ei, status); count_launch();
+  }
+  MPN_LAUNCH_CHECK();
+
+  const int tiles_out = (int)ceil_div(g->num_out, tc::TS);
+  const int tiles_in = (int)ceil_div(e - g->num_out, tc::TS);
+  const int pairs = (tiles_out + 1) / 2 + (tiles_in + 1) / 2;
+  int grid = sms;
+  if (grid > pairs) grid = pairs;
+  if (tiles_out > 0 && tiles_in > 0 && grid < 2) grid = 2;
+
+  for (int step = 1; step <= num_steps; ++step) {
+    const __half* xl_cur = m.xl[(step - 1) & 1];
+    __half* xl_next = m.xl[step & 1];
+    if (e > 0) {
+      tc::TcArgs a;
+      a.slot_row = g->slot_row; a.slot_col = g->slot_col; a.slot_edge = g->slot_edge;
+      a.num_edges = e; a.num_out = g->num_out; a.tiles_out = tiles_out; a.tiles_in = tiles_in;
+      a.xi = reinterpret_cast<const uint4*>(m.xi);
+      a.xl = reinterpret_cast<const uint4*>(xl_cur);
+      a.prow = m.prow;
+      a.ei = m.ei;
+      a.es_in = step == 1 ? m.ei : m.es;
+      a.es_out = m.es;
+      a.flow = m.flow; a.part = m.part;
+      a.logits = (logits && step >= first_class_step) ? logits + (int64_t)(step - first_class_step) * e : nullptr;
+      a.wimg_out = m.wimg_out; a.wimg_in = m.wimg_in;
+      a.status = status;
+      if (profiling()) profile_mark(0, true, s);
+      tc::mp_edge_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, s>>>(a); count_launch();
+      if (profiling()) profile_mark(0, false, s);
+    }
+    if (profiling()) profile_mark(1, true, s);
+    tc::node_tc_kernel<<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out, tiles_out, m.flow, m.part, w->node_w,
+                                             w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
+                                             step == num_steps ? x_out : nullptr, status);
+    count_launch();
+    if (profiling()) profile_mark(1, false, s);
+    MPN_LAUNCH_CHECK();
+  }
+  if (e_out && e > 0) {
+    const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div(e, 256), (int64_t)sms * 8);
+    tc::unsplit_edges_kernel<<<egrid, 256, 0, s>>>(m.es, e, e_out); count_launch();
+    MPN_LAUNCH_CHECK();
+  }
+  return MPN_OK;
+}
+
+}  // extern "C"

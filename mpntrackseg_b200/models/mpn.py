@@ -153,6 +153,8 @@ class MOTMPNet(nn.Module):
         self.MPNet = self._build_core_MPNet(model_params=model_params, encoder_feats_dict=enc)
         self.num_enc_steps = model_params['num_enc_steps']
         self.num_class_steps = model_params['num_class_steps']
+        # 'auto' | 'tc' | 'fp32' (None = $MPN_ENGINE or 'auto'), see ops.mp_forward
+        self.engine = None
 
     def _build_core_MPNet(self, model_params, encoder_feats_dict):
         """reference: models/mpn.py:250-317"""
@@ -209,7 +211,7 @@ class MOTMPNet(nn.Module):
         e0 = self.encode_edges(torch.cat(eas), layout)
         cw, keep = self.core_weights()
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
-        logits = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step)
+        logits = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, engine=self.engine)
         outs, eo = [], 0
         for _, e in sizes:
             outs.append({'classified_edges': [logits[i, eo:eo + e].view(-1, 1) for i in range(logits.shape[0])],
@@ -228,7 +230,8 @@ class MOTMPNet(nn.Module):
         e0 = self.encode_edges(edge_attr, layout)
         cw, keep = self.core_weights()
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
-        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, want_state=return_state)
+        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, want_state=return_state,
+                             engine=self.engine)
         logits = res[0] if return_state else res
         out = {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])],
                'mask_predictions': []}

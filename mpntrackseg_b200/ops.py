@@ -5,12 +5,18 @@ memory + stream plumbing only) and enqueues the library's kernels on torch's cur
 stream.  CPU tensors are rejected: there is no CPU fallback.
 """
 import ctypes as C
+import os
+import warnings
 from dataclasses import dataclass
 
 import torch
 
 from . import _cabi
 from ._cabi import CoreWeights, EdgeLayout, check, lib, ptr, stream_ptr
+
+
+# engine='tc' also checks the overflow status (one 4-byte device read) unless this is cleared
+STRICT_TC_STATUS = True
 
 
 def _req(t, dtype, name):
@@ -219,9 +225,24 @@ def core_weights(named):
     return cw, list(keep.values())
 
 
-def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False):
+ENGINES = ('auto', 'tc', 'fp32')
+
+
+def default_engine():
+    eng = os.environ.get('MPN_ENGINE', 'auto')
+    if eng not in ENGINES:
+        raise ValueError(f'MPN_ENGINE must be one of {ENGINES}, got {eng!r}')
+    return eng
+
+
+def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False, engine=None):
     """Run the step loop.  Returns logits [S, E] (original edge order) and, if asked, the final
-    node / edge latent states (edge state in slot order).  models/mpn.py:364-389"""
+    node / edge latent states (edge state in slot order).  models/mpn.py:364-389
+
+    engine: 'tc' = tcgen05 tensor-core kernels (fp16 hi/lo split operands, fp32 accumulate),
+    'fp32' = fp32 SIMT kernels, 'auto' (default) = 'tc', rerun on 'fp32' if an activation left
+    the fp16 range."""
+    engine = engine or default_engine()
     x_init = _req(x_init, torch.float32, 'x_init')
     e_init = _req(e_init, torch.float32, 'e_init')
     n, e, dev = layout.num_nodes, layout.num_edges, x_init.device
@@ -229,10 +250,25 @@ def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_sta
     n_cls = min(n_cls, max(num_steps, 1))
     first = max(first_class_step, 1)
     logits = torch.empty((n_cls, e), dtype=torch.float32, device=dev)
-    ws = _bytes(lib().mpn_mp_workspace(n, e), dev)
     x_out = torch.empty((n, cw.dn), dtype=torch.float32, device=dev) if want_state else None
     e_out = torch.empty((e, cw.de), dtype=torch.float32, device=dev) if want_state else None
     g = layout.c_struct()
+    use_tc = engine in ('auto', 'tc') and num_steps >= 1 and n > 0
+    if use_tc:
+        ws = _bytes(lib().mpn_mp_tc_workspace(n, e), dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib().mpn_mp_forward_tc(C.byref(cw), C.byref(g), ptr(x_init), ptr(e_init), int(num_steps), int(first),
+                                      ptr(ws), ptr(logits), ptr(x_out), ptr(e_out), ptr(status), stream_ptr()),
+              'mp_forward_tc')
+        if engine == 'tc' and not STRICT_TC_STATUS:
+            return (logits, x_out, e_out) if want_state else logits
+        if int(status.item()) == 0:
+            return (logits, x_out, e_out) if want_state else logits
+        if engine == 'tc':
+            raise OverflowError('mp_forward_tc: an activation left the fp16 range; use engine="fp32"')
+        warnings.warn('mpntrackseg_b200: activation outside the fp16 range, rerunning the message-passing '
+                      'steps on the fp32 kernels')
+    ws = _bytes(lib().mpn_mp_workspace(n, e), dev)
     check(lib().mpn_mp_forward(C.byref(cw), C.byref(g), ptr(x_init), ptr(e_init), int(num_steps), int(first),
                                ptr(ws), ptr(logits), ptr(x_out), ptr(e_out), stream_ptr()), 'mp_forward')
     return (logits, x_out, e_out) if want_state else logits

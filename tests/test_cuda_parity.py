@@ -32,9 +32,13 @@ def assert_logits_close(got, exp, what=''):
     assert ((pg > 0.5) == (pe > 0.5))[decisive].all(), f'{what}: binarised decisions differ'
 
 
-def make_model(mp, P):
+ENGINES = ('tc', 'fp32')
+
+
+def make_model(mp, P, engine=None):
     from mpntrackseg_b200.models.mpn import MOTMPNet
     model = MOTMPNet(mp).to(dev()).eval()
+    model.engine = engine
     core = {k: v for k, v in P.items() if k in model.state_dict()}
     model.load_state_dict(core, strict=True)
     return model
@@ -192,11 +196,12 @@ def test_edge_layout_rejects_self_loops():
 
 
 # ------------------------------------------------------------------ model
+@pytest.mark.parametrize('engine', ENGINES)
 @pytest.mark.parametrize('name', list(CASES))
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, engine):
     c = load_case(name)
     win, gold = c['win'], c['gold']
-    model = make_model(c['mp'], c['P'])
+    model = make_model(c['mp'], c['P'], engine)
     data = Data()
     data.x = win.x.to(dev())
     data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
@@ -216,12 +221,13 @@ def test_forward_matches_reference_golden(name):
     np.testing.assert_allclose(e_state.cpu().numpy(), gold['edge_state'], atol=2e-4 * scale, rtol=1e-3)
 
 
-def test_forward_is_deterministic_and_order_invariant():
+@pytest.mark.parametrize('engine', ENGINES)
+def test_forward_is_deterministic_and_order_invariant(engine):
     """No float atomics: two runs are bit-identical; permuting the caller's edge order
     permutes the logits and nothing else."""
     c = load_case('config1')
     win, gold = c['win'], c['gold']
-    model = make_model(c['mp'], c['P'])
+    model = make_model(c['mp'], c['P'], engine)
     ei = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
     ea = torch.from_numpy(gold['edge_attr']).to(dev())
     data = Data()
@@ -256,11 +262,12 @@ def test_metalayer_single_step_matches_oracle():
     np.testing.assert_allclose(x_new.cpu().numpy(), x_ref.numpy(), rtol=1e-4, atol=1e-3)
 
 
-def test_isolated_nodes_and_empty_graph():
+@pytest.mark.parametrize('engine', ENGINES)
+def test_isolated_nodes_and_empty_graph(engine):
     """Nodes without in- or out-edges aggregate to zero (scatter_add zero fill); E = 0 works."""
     mp = default_graph_model_params(3, 2)
     P = synth.make_params(mp, seed=2, gain=1.5, core_only=True)
-    model = make_model(mp, P)
+    model = make_model(mp, P, engine)
     g = torch.Generator().manual_seed(1)
     n = 9
     x = torch.randn(n, 2048, generator=g).abs()
@@ -281,7 +288,8 @@ def test_isolated_nodes_and_empty_graph():
         np.testing.assert_allclose(out['node_state'].cpu().numpy(), ref['node_state'].numpy(), rtol=1e-4, atol=1e-5)
 
 
-def test_config2_scale_against_oracle():
+@pytest.mark.parametrize('engine', ENGINES)
+def test_config2_scale_against_oracle(engine):
     """MOTS20-scale window (BASELINE config 2: 15 frames x 150 detections, k=50): full hot
     path on the GPU (graph build + forward) against the oracle on the same inputs."""
     from mpntrackseg_b200.data.mot_graph import MOTGraph
@@ -294,7 +302,7 @@ def test_config2_scale_against_oracle():
         ref = mpn_ref.mpn_forward(P, mp, win.x, ref_g['edge_index'], ref_g['edge_attr'])
     g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
     assert torch.equal(g.edge_index.cpu(), ref_g['edge_index'])
-    model = make_model(mp, P)
+    model = make_model(mp, P, engine)
     with torch.no_grad():
         out = model(g)
     got = torch.stack([t.view(-1) for t in out['classified_edges']]).cpu().numpy()
@@ -316,3 +324,21 @@ def test_encoders_against_torch():
     a, w = torch.randn(3, 5, generator=g), torch.randn(1, 5, generator=g)
     np.testing.assert_allclose(ops.linear(a.to(dev()), w.to(dev()), None, False).cpu().numpy(),
                                torch.nn.functional.linear(a, w).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_tc_engine_reports_fp16_overflow_and_auto_falls_back():
+    """Activations beyond the fp16 range: engine='tc' raises, 'auto' reruns on the fp32 kernels."""
+    c = load_case('kitti_shape')
+    win, gold = c['win'], c['gold']
+    P = {k: (v * 3.0 if k.endswith('weight') and k.startswith('MPNet') else v) for k, v in c['P'].items()}
+    data = Data()
+    data.x = win.x.to(dev())
+    data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    data.edge_attr = torch.from_numpy(gold['edge_attr']).to(dev())
+    with torch.no_grad():
+        ref = make_model(c['mp'], P, 'fp32')(data)['classified_edges'][-1]
+        with pytest.raises(OverflowError):
+            make_model(c['mp'], P, 'tc')(data)
+        with pytest.warns(UserWarning, match='fp16 range'):
+            auto = make_model(c['mp'], P, 'auto')(data)['classified_edges'][-1]
+    assert torch.equal(auto, ref)
