@@ -57,11 +57,16 @@ constexpr int C_D3 = 96;                    // layer-3 accumulator, 64 cols
 constexpr int C_A4H = 176, C_A4L = 208;     // layer-4 input hi / lo     (K = 64)
 constexpr int C_D4 = 0;                     // layer-4 accumulator, 32 cols (over the dead x[col])
 
+// ---- per-row sums are made per warp over its 32 consecutive slots ("chunk"); rows that cross a
+//      chunk boundary leave partial sums that the node kernel adds up in chunk order.
+constexpr int CHUNK = 32;
+
 // ---- dynamic shared memory map
 constexpr int MSG_LD = DN + 1;
-constexpr int SM_MSG = IMG_BYTES;                                   // float [2][TS*MSG_LD]
-constexpr int SM_ROWS = SM_MSG + 2 * TS * MSG_LD * 4;               // int   [2][TS+4]
-constexpr int SM_BAR = SM_ROWS + 2 * (TS + 4) * 4;                  // u64 a_ready[2], d_ready[2]
+constexpr int STAGE_ROW = 400;                                      // 24 x 16 B operands per edge + 16 B pad (bank spread)
+constexpr int SM_MSG = IMG_BYTES;                                   // float [8 warps][32*MSG_LD]
+constexpr int SM_STAGE = SM_MSG + 8 * CHUNK * MSG_LD * 4;           // [2 groups][TS][STAGE_ROW]  next tile's operands
+constexpr int SM_BAR = SM_STAGE + 2 * TS * STAGE_ROW;               // u64 a_ready[2], d_ready[2]
 constexpr int SM_TMEM = SM_BAR + 4 * 8;
 constexpr int SMEM_BYTES = SM_TMEM + 16;
 
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
 // Per step: x' = ReLU(Wn [flow_in | flow_out] + bn)  (models/mpn.py:97-99), then the split copy of
 // x' for the next step's gathers and prow[r] = pinit[r] + W0[:, 32:64] x'.
 __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
-                                                      int64_t num_nodes, int64_t num_out, int32_t tiles_out,
+                                                      int64_t num_nodes, int64_t num_out, int32_t chunks_out,
                                                       const float* __restrict__ flow, const float* __restrict__ part,
                                                       const float* __restrict__ node_w, const float* __restrict__ node_b,
                                                       const float* __restrict__ w0, const float* __restrict__ pinit,
@@ -202,17 +207,17 @@ __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict_
     for (int d = 0; d < 2; ++d) {
       const int32_t* ptr = d == 0 ? in_ptr : out_ptr;
       const int64_t seg_base = d == 0 ? num_out : 0;
-      const int tile_off = d == 0 ? tiles_out : 0;
+      const int64_t chunk_off = d == 0 ? chunks_out : 0;
       const int64_t s0 = ptr[r], s1 = ptr[r + 1];
       float v = 0.f;
       if (s1 > s0) {
-        const int64_t ta = (s0 - seg_base) / TS, tb = (s1 - 1 - seg_base) / TS;
-        if (ta == tb) {
+        const int64_t ca = (s0 - seg_base) / CHUNK, cb = (s1 - 1 - seg_base) / CHUNK;
+        if (ca == cb) {
           v = flow[r * 2 * DN + d * DN + lane];
         } else {
-          const bool first_in_tile = (s0 - seg_base) % TS == 0;
-          v = part[((tile_off + ta) * 2 + (first_in_tile ? 0 : 1)) * DN + lane];
-          for (int64_t t = ta + 1; t <= tb; ++t) v += part[((tile_off + t) * 2) * DN + lane];
+          const bool first_in_chunk = (s0 - seg_base) % CHUNK == 0;
+          v = part[((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN + lane];
+          for (int64_t t = ca + 1; t <= cb; ++t) v += part[((chunk_off + t) * 2) * DN + lane];
         }
       }
       fl[d] = v;
@@ -289,6 +294,7 @@ struct TcArgs {
   const int32_t* slot_row; const int32_t* slot_col; const int32_t* slot_edge;
   int64_t num_edges, num_out;
   int32_t tiles_out, tiles_in;
+  int64_t chunks_out;    // number of 32-slot chunks of the flow_out group
   const uint4* xi;       // [N][8]  x_init split rows (128 B)
   const uint4* xl;       // [N][8]  x_lat split rows
   const float* prow;     // [N][80] hoisted row term (incl. bias)
@@ -301,7 +307,7 @@ struct TcArgs {
 };
 
 // relu(acc + add) for 16 values, split to fp16 hi/lo words; accumulates the overflow detector
-__device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const float (&add)[16], uint32_t (&hi)[8],
+__device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const float* add, uint32_t (&hi)[8],
                                              uint32_t (&lo)[8], uint32_t& ovf) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -328,7 +334,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   const int tiles_dir = dir_out ? a.tiles_out : a.tiles_in;
   const int64_t seg_base = dir_out ? 0 : a.num_out;
   const int64_t seg_end = dir_out ? a.num_out : a.num_edges;
-  const int tile_off = dir_out ? 0 : a.tiles_out;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);     // a_ready[0..1], d_ready[2..3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
@@ -353,74 +358,108 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   if (warp < 8) {
     // ================================================================ epilogue groups
     const int g = warp >> 2;
+    const int wq = warp & 3;                                          // quarter of the tile = this warp's TMEM lanes
     const int gt = tid & (TS - 1);
-    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;
-    float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + g * TS * MSG_LD;
-    int32_t* s_rows = reinterpret_cast<int32_t*>(smem + SM_ROWS) + g * (TS + 4);
+    const uint32_t tlane = tbase + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * 256u;
+    float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + warp * CHUNK * MSG_LD;
+    const uint4* s_stage = reinterpret_cast<const uint4*>(smem + SM_STAGE + (g * TS + gt) * STAGE_ROW);
+    const uint32_t stage_addr = smem_u32(s_stage);
     uint64_t* a_ready = &bars[g];
     uint64_t* d_ready = &bars[2 + g];
+    const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
     uint32_t pd = 0;
     uint32_t ovf = 0;
-    for (int p = cta_in_dir; 2 * p + g < tiles_dir; p += ctas_in_dir) {
-      const int t = 2 * p + g;
-      const int64_t base = seg_base + (int64_t)t * TS;
-      const int cnt = (int)(seg_end - base < TS ? seg_end - base : TS);
+
+    // operands of one edge: x_init[c] (8 x 16 B), x_lat[c] (8), e_init (4), e (4) -> this thread's staging row
+    auto prefetch = [&](int32_t c, int64_t slot, bool first_step_alias) {
+      const uint4* pxi = a.xi + (int64_t)c * 8;
+      const uint4* pxl = a.xl + (int64_t)c * 8;
+      const uint4* pei = a.ei + slot * 4;
+      const uint4* pes = a.es_in + slot * 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cp_async16(stage_addr + 16 * j, pxi + j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cp_async16(stage_addr + 128 + 16 * j, pxl + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cp_async16(stage_addr + 256 + 16 * j, pei + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cp_async16(stage_addr + 320 + 16 * j, pes + j);
+      (void)first_step_alias;
+    };
+
+    int p = cta_in_dir;
+    bool have = 2 * p + g < tiles_dir;
+    int64_t base = 0, slot = 0;
+    int cnt = 0;
+    int32_t r = 0, c = 0;
+    if (have) {
+      base = seg_base + (int64_t)(2 * p + g) * TS;
+      cnt = (int)(seg_end - base < TS ? seg_end - base : TS);
+      slot = gt < cnt ? base + gt : base + cnt - 1;                   // clamp: loads stay in range
+      r = a.slot_row[slot];
+      c = a.slot_col[slot];
+      prefetch(c, slot, false);
+    }
+    while (have) {
       const bool valid = gt < cnt;
-      const int64_t slot = valid ? base + gt : base + cnt - 1;       // clamp: loads stay in range
-      const int32_t r = a.slot_row[slot], c = a.slot_col[slot];
-      s_rows[1 + gt] = valid ? r : -1;
-      if (gt == 0) {
-        s_rows[0] = base > seg_base ? a.slot_row[base - 1] : -1;
-        s_rows[TS + 1] = base + cnt < seg_end ? a.slot_row[base + cnt] : -1;
+      // ---- indices of this group's next tile (consumed after the load phase)
+      const int pn = p + ctas_in_dir;
+      const bool have_n = 2 * pn + g < tiles_dir;
+      int64_t base_n = 0, slot_n = 0;
+      int cnt_n = 0;
+      int32_t rn = 0, cn = 0;
+      if (have_n) {
+        base_n = seg_base + (int64_t)(2 * pn + g) * TS;
+        cnt_n = (int)(seg_end - base_n < TS ? seg_end - base_n : TS);
+        slot_n = gt < cnt_n ? base_n + gt : base_n + cnt_n - 1;
+        rn = a.slot_row[slot_n];
+        cn = a.slot_col[slot_n];
       }
-      // ---- operands of layer 1 (and the x[col] part of layer 3): global -> registers -> TMEM
+      // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
+      const int64_t cs = base + wq * CHUNK;
+      const int cw = cnt - wq * CHUNK < 0 ? 0 : (cnt - wq * CHUNK > CHUNK ? CHUNK : cnt - wq * CHUNK);
+      int32_t nb = -1;
+      if (lane == 0 && cw > 0 && cs > seg_base) nb = a.slot_row[cs - 1];
+      if (lane == 31 && cw == CHUNK && cs + CHUNK < seg_end) nb = a.slot_row[cs + CHUNK];
+
+      // ---- load phase: staged operands -> TMEM
+      cp_async_wait_all();
       {
-        const uint4* pxi = a.xi + (int64_t)c * 8;
-        const uint4* pxl = a.xl + (int64_t)c * 8;
-        const uint4* pei = a.ei + slot * 4;
-        const uint4* pes = a.es_in + slot * 4;
-        uint4 q[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = __ldg(pxi + j);
-        uint4 u[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = __ldg(pxl + j);
-        uint4 ev[4], es[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { ev[j] = __ldg(pei + j); es[j] = pes[j]; }
-        auto st2 = [&](int col, const uint4& x, const uint4& y) {
+        auto st2 = [&](int col, int j) {
+          const uint4 x = s_stage[j], y = s_stage[j + 1];
           const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
           tmem_st8(tlane + col, w8);
         };
-        st2(C_XCH + 0, q[0], q[1]);  st2(C_XCH + 8, q[2], q[3]);     // x_init hi
-        st2(C_XCL + 0, q[4], q[5]);  st2(C_XCL + 8, q[6], q[7]);     // x_init lo
-        st2(C_XCH + 16, u[0], u[1]); st2(C_XCH + 24, u[2], u[3]);    // x_lat hi
-        st2(C_XCL + 16, u[4], u[5]); st2(C_XCL + 24, u[6], u[7]);    // x_lat lo
-        st2(C_EH + 0, ev[0], ev[1]); st2(C_EL + 0, ev[2], ev[3]);    // e_init hi / lo
-        st2(C_EH + 8, es[0], es[1]); st2(C_EL + 8, es[2], es[3]);    // e hi / lo
+        st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
+        st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
+        st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
+        st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
+        st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
+        st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(a_ready);
+      if (have_n) prefetch(cn, slot_n, false);                        // staging row is free again
 
       // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand
       {
-        const float4* pr = reinterpret_cast<const float4*>(a.prow + (int64_t)r * EH);
+        float pr[EH];
+        const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)r * EH);
+#pragma unroll
+        for (int j = 0; j < EH / 4; ++j) {
+          const float4 v = __ldg(prp + j);
+          pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
+        }
         mbar_wait(d_ready, pd); pd ^= 1;
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < EH / 16; ++ch) {
           uint32_t acc[16];
           tmem_ld16(tlane + C_D1 + 16 * ch, acc);
-          float add[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = __ldg(pr + 4 * ch + j);
-            add[4 * j] = v.x; add[4 * j + 1] = v.y; add[4 * j + 2] = v.z; add[4 * j + 3] = v.w;
-          }
           tc_wait_ld();
           uint32_t hi[8], lo[8];
-          relu_split16(acc, add, hi, lo, ovf);
+          relu_split16(acc, pr + 16 * ch, hi, lo, ovf);
           tmem_st8(tlane + C_A2H + 8 * ch, hi);
           tmem_st8(tlane + C_A2L + 8 * ch, lo);
         }
@@ -489,7 +528,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         tc_fence_before();
         mbar_arrive(a_ready);
       }
-      // ---- epilogue 4: m = ReLU(D4 + fb1), per-row sums in slot order
+      // ---- epilogue 4: m = ReLU(D4 + fb1); per-row sums over this warp's 32 slots, in slot order
       {
         mbar_wait(d_ready, pd); pd ^= 1;
         tc_fence_after();
@@ -501,32 +540,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float m = fmaxf(__uint_as_float(acc[j]) + s_f[F_FB1 + 16 * ch + j], 0.f);
-            s_msg[gt * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
+            s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
           }
         }
         tc_fence_before();
-        named_barrier(1 + g, TS);
-        if ((warp & 3) == 0) {
-          const int f = lane;
+        __syncwarp();
+        if (cw > 0) {                                                 // warp-uniform
+          const int f = lane;                                         // lane = feature from here on
           const int dir_off = dir_out ? DN : 0;                       // cat(flow_in, flow_out), mpn.py:97
-          const int tile_id = tile_off + t;
-          int seg_first_t = 0;
-          int32_t cur = s_rows[1];
+          const int64_t chunk_id = chunk_off + (cs - seg_base) / CHUNK;
+          const int32_t r_prev = __shfl_sync(0xffffffffu, nb, 0);
+          const int32_t r_next = __shfl_sync(0xffffffffu, nb, 31);
+          float mv[CHUNK];
+#pragma unroll
+          for (int q = 0; q < CHUNK; ++q) mv[q] = s_msg[q * MSG_LD + f];
+          int seg_first = 0;
+          int32_t cur = __shfl_sync(0xffffffffu, r, 0);
           float sum = 0.f;
-          for (int q = 0; q <= cnt; ++q) {
-            const int32_t rq = q < cnt ? s_rows[1 + q] : -2;
+#pragma unroll
+          for (int q = 0; q <= CHUNK; ++q) {
+            int32_t rq = -2;
+            if (q < CHUNK) { rq = __shfl_sync(0xffffffffu, r, q); if (q >= cw) rq = -2; }
             if (rq != cur) {
-              const bool starts_before = seg_first_t == 0 && s_rows[0] == cur;
-              const bool continues = q == cnt && s_rows[TS + 1] == cur;
-              if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
-              else a.part[((int64_t)tile_id * 2 + (seg_first_t == 0 ? 0 : 1)) * DN + f] = sum;
-              cur = rq; sum = 0.f; seg_first_t = q;
+              if (cur >= 0) {
+                const bool starts_before = seg_first == 0 && r_prev == cur;
+                const bool continues = q == cw && r_next == cur;
+                if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
+                else a.part[(chunk_id * 2 + (seg_first == 0 ? 0 : 1)) * DN + f] = sum;
+              }
+              cur = rq; sum = 0.f; seg_first = q;
             }
-            if (q < cnt) sum += s_msg[q * MSG_LD + f];
+            if (q < CHUNK) sum += mv[q];
           }
         }
-        named_barrier(1 + g, TS);
+        __syncwarp();
       }
+      p = pn; have = have_n; base = base_n; cnt = cnt_n; slot = slot_n; r = rn; c = cn;
     }
     if (ovf & 0x80008000u) atomicOr(a.status, 1);
   } else if (lane == 0) {
@@ -595,7 +644,7 @@ struct TcWorkspace {
 
 static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   Carver cv(ws);
-  const int64_t tiles = ceil_div(e, TS) + 2;
+  const int64_t chunks = ceil_div(e, CHUNK) + 8;
   TcWorkspace w;
   w.xi = cv.take<__half>(n * 64);
   w.xl[0] = cv.take<__half>(n * 64);
@@ -605,7 +654,7 @@ static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   w.ei = cv.take<uint4>(e * 4);
   w.es = cv.take<uint4>(e * 4);
   w.flow = cv.take<float>(n * 2 * DN);
-  w.part = cv.take<float>(tiles * 2 * DN);
+  w.part = cv.take<float>(chunks * 2 * DN);
   w.wimg_out = cv.take<uint8_t>(IMG_BYTES);
   w.wimg_in = cv.take<uint8_t>(IMG_BYTES);
   if (out) *out = w;
@@ -669,6 +718,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       tc::TcArgs a;
       a.slot_row = g->slot_row; a.slot_col = g->slot_col; a.slot_edge = g->slot_edge;
       a.num_edges = e; a.num_out = g->num_out; a.tiles_out = tiles_out; a.tiles_in = tiles_in;
+      a.chunks_out = ceil_div(g->num_out, tc::CHUNK);
       a.xi = reinterpret_cast<const uint4*>(m.xi);
       a.xl = reinterpret_cast<const uint4*>(xl_cur);
       a.prow = m.prow;
@@ -684,7 +734,8 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       if (profiling()) profile_mark(0, false, s);
     }
     if (profiling()) profile_mark(1, true, s);
-    tc::node_tc_kernel<<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out, tiles_out, m.flow, m.part, w->node_w,
+    tc::node_tc_kernel<<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
+                                             (int32_t)ceil_div(g->num_out, tc::CHUNK), m.flow, m.part, w->node_w,
                                              w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
                                              step == num_steps ? x_out : nullptr, status);
     count_launch();
