@@ -304,7 +304,23 @@ struct TcArgs {
   float* flow; float* part; float* logits;
   const uint8_t* wimg_out; const uint8_t* wimg_in;
   int32_t* status;
+  long long* trace;      // optional [16 stamps x 64 tiles] cycle trace of CTA 0 / group 0 (development)
 };
+
+__device__ __forceinline__ void ld_f32x16(float (&d)[16], const float* __restrict__ p) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+    d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void ld_f32x8(float (&d)[8], const float* __restrict__ p) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+    d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+  }
+}
 
 // relu(acc + add) for 16 values, split to fp16 hi/lo words; accumulates the overflow detector
 __device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const float* add, uint32_t (&hi)[8],
@@ -370,21 +386,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
     uint32_t pd = 0;
     uint32_t ovf = 0;
 
-    // operands of one edge: x_init[c] (8 x 16 B), x_lat[c] (8), e_init (4), e (4) -> this thread's staging row
-    auto prefetch = [&](int32_t c, int64_t slot, bool first_step_alias) {
-      const uint4* pxi = a.xi + (int64_t)c * 8;
-      const uint4* pxl = a.xl + (int64_t)c * 8;
-      const uint4* pei = a.ei + slot * 4;
-      const uint4* pes = a.es_in + slot * 4;
+    // Operands of the warp's 32 edges -> their staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at
+    // +128, e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole
+    // 128-B lines: 8 lanes x 16 B per node row, 4 lanes x 16 B per edge row.
+    const uint32_t stage_warp = smem_u32(smem + SM_STAGE + (g * TS + wq * CHUNK) * STAGE_ROW);
+    auto prefetch = [&](int32_t c, int64_t chunk_slot0, int64_t last_slot) {
+      const int sub8 = lane >> 3, pc8 = lane & 7;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cp_async16(stage_addr + 16 * j, pxi + j);
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + sub8;
+        const int32_t cr = __shfl_sync(0xffffffffu, c, row);
+        cp_async16(stage_warp + row * STAGE_ROW + pc8 * 16, a.xi + (int64_t)cr * 8 + pc8);
+        cp_async16(stage_warp + row * STAGE_ROW + 128 + pc8 * 16, a.xl + (int64_t)cr * 8 + pc8);
+      }
+      const int sub4 = lane >> 2, pc4 = lane & 3;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cp_async16(stage_addr + 128 + 16 * j, pxl + j);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cp_async16(stage_addr + 256 + 16 * j, pei + j);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cp_async16(stage_addr + 320 + 16 * j, pes + j);
-      (void)first_step_alias;
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 8 + sub4;
+        int64_t sl = chunk_slot0 + row;
+        sl = sl < last_slot ? sl : last_slot;                          // clamp: loads stay in range
+        cp_async16(stage_warp + row * STAGE_ROW + 256 + pc4 * 16, a.ei + sl * 4 + pc4);
+        cp_async16(stage_warp + row * STAGE_ROW + 320 + pc4 * 16, a.es_in + sl * 4 + pc4);
+      }
     };
 
     int p = cta_in_dir;
@@ -398,10 +421,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
       slot = gt < cnt ? base + gt : base + cnt - 1;                   // clamp: loads stay in range
       r = a.slot_row[slot];
       c = a.slot_col[slot];
-      prefetch(c, slot, false);
+      prefetch(c, base + wq * CHUNK, base + cnt - 1);
     }
+    int trace_i = 0;
+#define TC_STAMP(k) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && trace_i < 64) a.trace[trace_i * 16 + (k)] = clock64(); } while (0)
     while (have) {
       const bool valid = gt < cnt;
+      TC_STAMP(0);
       // ---- indices of this group's next tile (consumed after the load phase)
       const int pn = p + ctas_in_dir;
       const bool have_n = 2 * pn + g < tiles_dir;
@@ -424,6 +450,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
 
       // ---- load phase: staged operands -> TMEM
       cp_async_wait_all();
+      __syncwarp();                                                   // rows were fetched by other lanes
+      TC_STAMP(1);
       {
         auto st2 = [&](int col, int j) {
           const uint4 x = s_stage[j], y = s_stage[j + 1];
@@ -440,7 +468,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(a_ready);
-      if (have_n) prefetch(cn, slot_n, false);                        // staging row is free again
+      TC_STAMP(2);
+      __syncwarp();                                                   // the warp's staging rows are free again
+      if (have_n) prefetch(cn, base_n + wq * CHUNK, base_n + cnt_n - 1);
 
       // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand
       {
@@ -451,7 +481,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
           const float4 v = __ldg(prp + j);
           pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
         }
+        TC_STAMP(3);
         mbar_wait(d_ready, pd); pd ^= 1;
+        TC_STAMP(4);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < EH / 16; ++ch) {
@@ -466,16 +498,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(a_ready);
+        TC_STAMP(5);
       }
       // ---- epilogue 2: e' = ReLU(D2 + b1) -> state, layer-3 operand, classifier
       {
         mbar_wait(d_ready, pd); pd ^= 1;
+        TC_STAMP(6);
         tc_fence_after();
         uint32_t acc[16];
         tmem_ld16(tlane + C_D2, acc);
         float add[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) add[j] = s_f[F_B1 + j];
+        ld_f32x16(add, s_f + F_B1);
         tc_wait_ld();
         uint32_t hi[8], lo[8];
         relu_split16(acc, add, hi, lo, ovf);
@@ -484,6 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(a_ready);
+        TC_STAMP(7);
         if (valid) {
           uint4* dst = a.es_out + (base + gt) * 4;
           dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -491,33 +525,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
           dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           if (a.logits != nullptr) {                                  // classifier 16 -> 8 -> 1 (fp32)
-            float hc[CH];
-#pragma unroll
-            for (int o = 0; o < CH; ++o) hc[o] = s_f[F_CB0 + o];
+            float hc[CH], wv[CH];
+            ld_f32x8(hc, s_f + F_CB0);
 #pragma unroll
             for (int i = 0; i < DE; ++i) {
               const float ei = fmaxf(__uint_as_float(acc[i]) + add[i], 0.f);
+              ld_f32x8(wv, s_f + F_CW0 + i * CH);
 #pragma unroll
-              for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, s_f[F_CW0 + i * CH + o], hc[o]);
+              for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, wv[o], hc[o]);
             }
+            ld_f32x8(wv, s_f + F_CW1);
             float lg = s_f[F_CB1];
 #pragma unroll
-            for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), s_f[F_CW1 + o], lg);
+            for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), wv[o], lg);
             a.logits[a.slot_edge[base + gt]] = lg;
           }
         }
       }
       // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand
       {
+        TC_STAMP(8);
         mbar_wait(d_ready, pd); pd ^= 1;
+        TC_STAMP(9);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < FHP / 16; ++ch) {
           uint32_t acc[16];
           tmem_ld16(tlane + C_D3 + 16 * ch, acc);
           float add[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) add[j] = s_f[F_FB0 + 16 * ch + j];
+          ld_f32x16(add, s_f + F_FB0 + 16 * ch);
           tc_wait_ld();
           uint32_t hi[8], lo[8];
           relu_split16(acc, add, hi, lo, ovf);
@@ -527,19 +563,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(a_ready);
+        TC_STAMP(10);
       }
       // ---- epilogue 4: m = ReLU(D4 + fb1); per-row sums over this warp's 32 slots, in slot order
       {
         mbar_wait(d_ready, pd); pd ^= 1;
+        TC_STAMP(11);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < DN / 16; ++ch) {
           uint32_t acc[16];
           tmem_ld16(tlane + C_D4 + 16 * ch, acc);
+          float add[16];
+          ld_f32x16(add, s_f + F_FB1 + 16 * ch);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float m = fmaxf(__uint_as_float(acc[j]) + s_f[F_FB1 + 16 * ch + j], 0.f);
+            const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
             s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
           }
         }
@@ -551,81 +591,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
           const int64_t chunk_id = chunk_off + (cs - seg_base) / CHUNK;
           const int32_t r_prev = __shfl_sync(0xffffffffu, nb, 0);
           const int32_t r_next = __shfl_sync(0xffffffffu, nb, 31);
-          float mv[CHUNK];
-#pragma unroll
-          for (int q = 0; q < CHUNK; ++q) mv[q] = s_msg[q * MSG_LD + f];
-          int seg_first = 0;
-          int32_t cur = __shfl_sync(0xffffffffu, r, 0);
-          float sum = 0.f;
-#pragma unroll
-          for (int q = 0; q <= CHUNK; ++q) {
-            int32_t rq = -2;
-            if (q < CHUNK) { rq = __shfl_sync(0xffffffffu, r, q); if (q >= cw) rq = -2; }
-            if (rq != cur) {
-              if (cur >= 0) {
-                const bool starts_before = seg_first == 0 && r_prev == cur;
-                const bool continues = q == cw && r_next == cur;
-                if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
-                else a.part[(chunk_id * 2 + (seg_first == 0 ? 0 : 1)) * DN + f] = sum;
-              }
-              cur = rq; sum = 0.f; seg_first = q;
-            }
-            if (q < CHUNK) sum += mv[q];
+          const int32_t r_after = __shfl_down_sync(0xffffffffu, r, 1);
+          const bool seg_end_here = lane < cw && (lane == cw - 1 || r_after != r);
+          unsigned ends = __ballot_sync(0xffffffffu, seg_end_here);     // bit q: slot q closes a row segment
+          int s0 = 0;
+          while (ends) {                                               // warp-uniform
+            const int e1 = __ffs(ends) - 1;
+            ends &= ends - 1;
+            const int32_t cur = __shfl_sync(0xffffffffu, r, e1);
+            float sum = 0.f;
+            for (int q = s0; q <= e1; ++q) sum += s_msg[q * MSG_LD + f];
+            const bool starts_before = s0 == 0 && r_prev == cur;
+            const bool continues = e1 == cw - 1 && r_next == cur;
+            if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
+            else a.part[(chunk_id * 2 + (s0 == 0 ? 0 : 1)) * DN + f] = sum;
+            s0 = e1 + 1;
           }
         }
         __syncwarp();
+        TC_STAMP(12);
+        ++trace_i;
       }
       p = pn; have = have_n; base = base_n; cnt = cnt_n; slot = slot_n; r = rn; c = cn;
     }
     if (ovf & 0x80008000u) atomicOr(a.status, 1);
-  } else if (lane == 0) {
-    // ================================================================ MMA issuer (one thread)
-    const uint32_t img = smem_u32(smem);
-    uint32_t pa[2] = {0, 0};
+  } else {
+    // ================================================================ MMA issuer (warp 8, one elected lane issues)
+    // The whole warp runs the (uniform) scheduling loop so that every MMA operand lives in a uniform
+    // register; only the tcgen05.mma / commit instructions are predicated on the elected lane.
+    // Serves whichever group has its next layer's operands ready (no head-of-line blocking), so the
+    // two tiles in flight drift apart and one group's epilogue overlaps the other's MMAs.
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint64_t dbase = smem_desc_kmajor(smem_u32(smem), 128, 256);  // + (byte offset >> 4) per slab
     const uint32_t id80 = idesc_f16(128, EH), id16 = idesc_f16(128, DE), id64 = idesc_f16(128, FHP),
                    id32 = idesc_f16(128, DN);
-    auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, bool first) {
-      const uint64_t dh = smem_desc_kmajor(bh, 128, 256), dl = smem_desc_kmajor(bl, 128, 256);
-      mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
-      mma_ts(d, ah, dl, idesc, 1u);
-      mma_ts(d, al, dh, idesc, 1u);
-    };
-    for (int p = cta_in_dir; 2 * p < tiles_dir; p += ctas_in_dir) {
-      for (int layer = 1; layer <= 4; ++layer) {
-        for (int g = 0; g < 2; ++g) {
-          if (2 * p + g >= tiles_dir) continue;
-          const uint32_t cb = tbase + (uint32_t)g * 256u;
-          mbar_wait(&bars[g], pa[g]); pa[g] ^= 1;
-          tc_fence_after();
-          if (layer == 1) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              step3(cb + C_D1, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, img + OFF_L1H + ks * L1_SLAB,
-                    img + OFF_L1L + ks * L1_SLAB, id80, ks == 0);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              step3(cb + C_D1, cb + C_EH + 8 * ks, cb + C_EL + 8 * ks, img + OFF_L1H + (4 + ks) * L1_SLAB,
-                    img + OFF_L1L + (4 + ks) * L1_SLAB, id80, false);
-          } else if (layer == 2) {
-#pragma unroll
-            for (int ks = 0; ks < L2_KS; ++ks)
-              step3(cb + C_D2, cb + C_A2H + 8 * ks, cb + C_A2L + 8 * ks, img + OFF_L2H + ks * L2_SLAB,
-                    img + OFF_L2L + ks * L2_SLAB, id16, ks == 0);
-          } else if (layer == 3) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              step3(cb + C_D3, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, img + OFF_L3H + ks * L3_SLAB,
-                    img + OFF_L3L + ks * L3_SLAB, id64, ks == 0);
-            step3(cb + C_D3, cb + C_A3H, cb + C_A3L, img + OFF_L3H + 4 * L3_SLAB, img + OFF_L3L + 4 * L3_SLAB, id64, false);
-          } else {
-#pragma unroll
-            for (int ks = 0; ks < L4_KS; ++ks)
-              step3(cb + C_D4, cb + C_A4H + 8 * ks, cb + C_A4L + 8 * ks, img + OFF_L4H + ks * L4_SLAB,
-                    img + OFF_L4L + ks * L4_SLAB, id32, ks == 0);
-          }
-          mma_commit(&bars[2 + g]);
-        }
+    auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+      const uint64_t dh = dbase + (uint64_t)(off_h >> 4), dl = dbase + (uint64_t)(off_l >> 4);
+      if (elect_one()) {
+        mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
+        mma_ts(d, ah, dl, idesc, 1u);
+        mma_ts(d, al, dh, idesc, 1u);
       }
+    };
+    int pg[2] = {cta_in_dir, cta_in_dir};          // pair index each group works on
+    int layer[2] = {1, 1};
+    uint32_t pa[2] = {0, 0};
+    bool live[2] = {2 * pg[0] + 0 < tiles_dir, 2 * pg[1] + 1 < tiles_dir};
+    int g = 0;
+    while (live[0] || live[1]) {
+      const bool ready = live[g] && __shfl_sync(0xffffffffu, (int)mbar_test(&bars[g], pa[g]), 0) != 0;
+      if (!ready) { g ^= 1; continue; }
+      pa[g] ^= 1;
+      tc_fence_after();
+      const uint32_t cb = tb + (uint32_t)g * 256u;
+      if (layer[g] == 1) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          step3(cb + C_D1, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB,
+                id80, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          step3(cb + C_D1, cb + C_EH + 8 * ks, cb + C_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB,
+                OFF_L1L + (4 + ks) * L1_SLAB, id80, false);
+      } else if (layer[g] == 2) {
+#pragma unroll
+        for (int ks = 0; ks < L2_KS; ++ks)
+          step3(cb + C_D2, cb + C_A2H + 8 * ks, cb + C_A2L + 8 * ks, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
+                id16, ks == 0);
+      } else if (layer[g] == 3) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          step3(cb + C_D3, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB,
+                id64, ks == 0);
+        step3(cb + C_D3, cb + C_A3H, cb + C_A3L, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, id64, false);
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < L4_KS; ++ks)
+          step3(cb + C_D4, cb + C_A4H + 8 * ks, cb + C_A4L + 8 * ks, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
+                id32, ks == 0);
+      }
+      if (elect_one()) mma_commit(&bars[2 + g]);
+      __syncwarp();
+      if (++layer[g] == 5) {
+        layer[g] = 1;
+        pg[g] += ctas_in_dir;
+        live[g] = 2 * pg[g] + g < tiles_dir;
+      }
+      g ^= 1;
     }
   }
   __syncwarp();
@@ -633,6 +685,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   __syncthreads();
   if (warp == 8) tmem_dealloc<512>(tbase);
 }
+
+long long* g_trace = nullptr;   // set by mpn_tc_set_trace (development only)
 
 struct TcWorkspace {
   __half* xi; __half* xl[2];
@@ -667,6 +721,9 @@ static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
 using namespace mpn;
 
 extern "C" {
+
+/* development hook (not in the public header): device buffer of 64*16 int64 for a cycle trace */
+void mpn_tc_set_trace(long long* d_buf) { tc::g_trace = d_buf; }
 
 int64_t mpn_mp_tc_workspace(int64_t n, int64_t e) {
   return tc::carve(nullptr, n > 0 ? n : 1, e > 0 ? e : 1, nullptr) + 256;
@@ -729,6 +786,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       a.logits = (logits && step >= first_class_step) ? logits + (int64_t)(step - first_class_step) * e : nullptr;
       a.wimg_out = m.wimg_out; a.wimg_in = m.wimg_in;
       a.status = status;
+      a.trace = (step == 2) ? tc::g_trace : nullptr;
       if (profiling()) profile_mark(0, true, s);
       tc::mp_edge_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, s>>>(a); count_launch();
       if (profiling()) profile_mark(0, false, s);
