@@ -17,9 +17,11 @@
 // 64 B = [hi(16) | lo(16)], so loads are plain copies into TMEM and the bytes per edge-update
 // stay at 200.
 //
-// Warp roles (288 threads, 1 CTA / SM): warps 0-3 = epilogue group 0, warps 4-7 = group 1 (two
-// tiles in flight, each owns 256 of the 512 TMEM columns), warp 8 = TMEM allocator + the single
-// MMA-issuing thread.  While one group runs an epilogue the tensor core runs the other's layer.
+// Warp roles (256 threads, 1 CTA / SM): warps 0-3 = group 0, warps 4-7 = group 1; each group keeps
+// one tile in flight and owns 256 of the 512 TMEM columns.  After a group's 128 threads have
+// written a layer's operand, an elected lane of the group's first warp issues that layer's MMAs and
+// commits them to the group's mbarrier; while one group runs an epilogue the tensor core runs the
+// other group's layer.  Operand rows of the next tile are staged with cp.async during the current one.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,7 +32,7 @@ using namespace ptx;
 
 constexpr int TS = 128;
 constexpr int DN = 32, DE = 16, EH = 80, FH = 56, FHP = 64, CH = 8;
-constexpr int NTHREADS = 288;
+constexpr int NTHREADS = 256;
 
 // ---- shared-memory weight image (bytes). Slab = one K=16 step of a B operand: [n/8][k/8][n%8][8 halfs]
 constexpr int L1_KS = 6, L1_SLAB = EH * 32;
@@ -46,15 +48,13 @@ constexpr int F_B1 = 0, F_FB0 = F_B1 + DE, F_FB1 = F_FB0 + FHP, F_CW0 = F_FB1 + 
               F_CW1 = F_CB0 + CH, F_CB1 = F_CW1 + CH, F_COUNT = F_CB1 + 4;
 constexpr int IMG_BYTES = (OFF_F32 + F_COUNT * 4 + 127) / 128 * 128;
 
-// ---- TMEM column map inside a group's 256 columns
+// ---- TMEM column map inside a group's 256 columns.  Each epilogue rewrites an accumulator chunk of
+//      16 fp32 columns IN PLACE as the next layer's operand: [hi: 8 cols of fp16 pairs | lo: 8 cols].
 constexpr int C_XCH = 0, C_XCL = 32;        // x[col] hi / lo            (K = 64)
 constexpr int C_EH = 64, C_EL = 80;         // [e_init | e] hi / lo      (K = 32)
-constexpr int C_D1 = 96;                    // layer-1 accumulator, 80 cols
-constexpr int C_A2H = 176, C_A2L = 216;     // layer-2 input hi / lo     (K = 80)
-constexpr int C_D2 = 64;                    // layer-2 accumulator, 16 cols (over the dead E region)
-constexpr int C_A3H = 80, C_A3L = 88;       // e' hi / lo                (K = 16)
-constexpr int C_D3 = 96;                    // layer-3 accumulator, 64 cols
-constexpr int C_A4H = 176, C_A4L = 208;     // layer-4 input hi / lo     (K = 64)
+constexpr int C_D1 = 96, C_A2 = C_D1;       // layer-1 accumulator (80 cols) -> layer-2 operand (K = 80)
+constexpr int C_D2 = 64, C_A3 = C_D2;       // layer-2 accumulator (16 cols, over the dead E region) -> e' operand
+constexpr int C_D3 = 176, C_A4 = C_D3;      // layer-3 accumulator (64 cols) -> layer-4 operand (K = 64)
 constexpr int C_D4 = 0;                     // layer-4 accumulator, 32 cols (over the dead x[col])
 
 // ---- per-row sums are made per warp over its 32 consecutive slots ("chunk"); rows that cross a
@@ -66,7 +66,7 @@ constexpr int MSG_LD = DN + 1;
 constexpr int STAGE_ROW = 400;                                      // 24 x 16 B operands per edge + 16 B pad (bank spread)
 constexpr int SM_MSG = IMG_BYTES;                                   // float [8 warps][32*MSG_LD]
 constexpr int SM_STAGE = SM_MSG + 8 * CHUNK * MSG_LD * 4;           // [2 groups][TS][STAGE_ROW]  next tile's operands
-constexpr int SM_BAR = SM_STAGE + 2 * TS * STAGE_ROW;               // u64 a_ready[2], d_ready[2]
+constexpr int SM_BAR = SM_STAGE + 2 * TS * STAGE_ROW;               // u64 d_ready[2] (+2 spare)
 constexpr int SM_TMEM = SM_BAR + 4 * 8;
 constexpr int SMEM_BYTES = SM_TMEM + 16;
 
@@ -336,7 +336,8 @@ __device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const fl
 
 __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
 
   // CTAs [0, n_out_ctas) walk flow_out tiles, the rest walk flow_in tiles.
   const int total_tiles = a.tiles_out + a.tiles_in;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   const int64_t seg_base = dir_out ? 0 : a.num_out;
   const int64_t seg_end = dir_out ? a.num_out : a.num_edges;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);     // a_ready[0..1], d_ready[2..3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);       // d_ready[group]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
   {
     const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
@@ -359,11 +360,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
     for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
-    mbar_init(&bars[0], TS); mbar_init(&bars[1], TS);
-    mbar_init(&bars[2], 1);  mbar_init(&bars[3], 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -371,319 +372,299 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   const uint32_t tbase = *tmem_slot;
   const float* s_f = reinterpret_cast<const float*>(smem + OFF_F32);
 
-  if (warp < 8) {
-    // ================================================================ epilogue groups
-    const int g = warp >> 2;
-    const int wq = warp & 3;                                          // quarter of the tile = this warp's TMEM lanes
-    const int gt = tid & (TS - 1);
-    const uint32_t tlane = tbase + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * 256u;
-    float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + warp * CHUNK * MSG_LD;
-    const uint4* s_stage = reinterpret_cast<const uint4*>(smem + SM_STAGE + (g * TS + gt) * STAGE_ROW);
-    const uint32_t stage_addr = smem_u32(s_stage);
-    uint64_t* a_ready = &bars[g];
-    uint64_t* d_ready = &bars[2 + g];
-    const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
-    uint32_t pd = 0;
-    uint32_t ovf = 0;
+  // Two groups of 4 warps, one 128-edge tile in flight each; a group owns 256 TMEM columns.
+  const int g = warp >> 2;
+  const int wq = warp & 3;                                            // quarter of the tile = this warp's TMEM lanes
+  const int gt = tid & (TS - 1);
+  const uint32_t tcol = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u;   // uniform: MMA operand base
+  const uint32_t tlane = tcol + ((uint32_t)(wq * 32) << 16);
+  float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + warp * CHUNK * MSG_LD;
+  const uint32_t stage_warp = smem_u32(smem + SM_STAGE + (g * TS + wq * CHUNK) * STAGE_ROW);
+  const uint4* s_stage = reinterpret_cast<const uint4*>(smem + SM_STAGE + (g * TS + gt) * STAGE_ROW);
+  uint64_t* d_ready = &bars[g];
+  const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
+  const int dir_off = dir_out ? DN : 0;                               // cat(flow_in, flow_out), mpn.py:97
+  uint32_t pd = 0;
+  uint32_t ovf = 0;
 
-    // Operands of the warp's 32 edges -> their staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at
-    // +128, e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole
-    // 128-B lines: 8 lanes x 16 B per node row, 4 lanes x 16 B per edge row.
-    const uint32_t stage_warp = smem_u32(smem + SM_STAGE + (g * TS + wq * CHUNK) * STAGE_ROW);
-    auto prefetch = [&](int32_t c, int64_t chunk_slot0, int64_t last_slot) {
-      const int sub8 = lane >> 3, pc8 = lane & 7;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = i * 4 + sub8;
-        const int32_t cr = __shfl_sync(0xffffffffu, c, row);
-        cp_async16(stage_warp + row * STAGE_ROW + pc8 * 16, a.xi + (int64_t)cr * 8 + pc8);
-        cp_async16(stage_warp + row * STAGE_ROW + 128 + pc8 * 16, a.xl + (int64_t)cr * 8 + pc8);
-      }
-      const int sub4 = lane >> 2, pc4 = lane & 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = i * 8 + sub4;
-        int64_t sl = chunk_slot0 + row;
-        sl = sl < last_slot ? sl : last_slot;                          // clamp: loads stay in range
-        cp_async16(stage_warp + row * STAGE_ROW + 256 + pc4 * 16, a.ei + sl * 4 + pc4);
-        cp_async16(stage_warp + row * STAGE_ROW + 320 + pc4 * 16, a.es_in + sl * 4 + pc4);
-      }
-    };
-
-    int p = cta_in_dir;
-    bool have = 2 * p + g < tiles_dir;
-    int64_t base = 0, slot = 0;
-    int cnt = 0;
-    int32_t r = 0, c = 0;
-    if (have) {
-      base = seg_base + (int64_t)(2 * p + g) * TS;
-      cnt = (int)(seg_end - base < TS ? seg_end - base : TS);
-      slot = gt < cnt ? base + gt : base + cnt - 1;                   // clamp: loads stay in range
-      r = a.slot_row[slot];
-      c = a.slot_col[slot];
-      prefetch(c, base + wq * CHUNK, base + cnt - 1);
-    }
-    int trace_i = 0;
-#define TC_STAMP(k) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && trace_i < 64) a.trace[trace_i * 16 + (k)] = clock64(); } while (0)
-    while (have) {
-      const bool valid = gt < cnt;
-      TC_STAMP(0);
-      // ---- indices of this group's next tile (consumed after the load phase)
-      const int pn = p + ctas_in_dir;
-      const bool have_n = 2 * pn + g < tiles_dir;
-      int64_t base_n = 0, slot_n = 0;
-      int cnt_n = 0;
-      int32_t rn = 0, cn = 0;
-      if (have_n) {
-        base_n = seg_base + (int64_t)(2 * pn + g) * TS;
-        cnt_n = (int)(seg_end - base_n < TS ? seg_end - base_n : TS);
-        slot_n = gt < cnt_n ? base_n + gt : base_n + cnt_n - 1;
-        rn = a.slot_row[slot_n];
-        cn = a.slot_col[slot_n];
-      }
-      // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
-      const int64_t cs = base + wq * CHUNK;
-      const int cw = cnt - wq * CHUNK < 0 ? 0 : (cnt - wq * CHUNK > CHUNK ? CHUNK : cnt - wq * CHUNK);
-      int32_t nb = -1;
-      if (lane == 0 && cw > 0 && cs > seg_base) nb = a.slot_row[cs - 1];
-      if (lane == 31 && cw == CHUNK && cs + CHUNK < seg_end) nb = a.slot_row[cs + CHUNK];
-
-      // ---- load phase: staged operands -> TMEM
-      cp_async_wait_all();
-      __syncwarp();                                                   // rows were fetched by other lanes
-      TC_STAMP(1);
-      {
-        auto st2 = [&](int col, int j) {
-          const uint4 x = s_stage[j], y = s_stage[j + 1];
-          const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-          tmem_st8(tlane + col, w8);
-        };
-        st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
-        st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
-        st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
-        st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
-        st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
-        st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(a_ready);
-      TC_STAMP(2);
-      __syncwarp();                                                   // the warp's staging rows are free again
-      if (have_n) prefetch(cn, base_n + wq * CHUNK, base_n + cnt_n - 1);
-
-      // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand
-      {
-        float pr[EH];
-        const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)r * EH);
-#pragma unroll
-        for (int j = 0; j < EH / 4; ++j) {
-          const float4 v = __ldg(prp + j);
-          pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
-        }
-        TC_STAMP(3);
-        mbar_wait(d_ready, pd); pd ^= 1;
-        TC_STAMP(4);
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < EH / 16; ++ch) {
-          uint32_t acc[16];
-          tmem_ld16(tlane + C_D1 + 16 * ch, acc);
-          tc_wait_ld();
-          uint32_t hi[8], lo[8];
-          relu_split16(acc, pr + 16 * ch, hi, lo, ovf);
-          tmem_st8(tlane + C_A2H + 8 * ch, hi);
-          tmem_st8(tlane + C_A2L + 8 * ch, lo);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(a_ready);
-        TC_STAMP(5);
-      }
-      // ---- epilogue 2: e' = ReLU(D2 + b1) -> state, layer-3 operand, classifier
-      {
-        mbar_wait(d_ready, pd); pd ^= 1;
-        TC_STAMP(6);
-        tc_fence_after();
-        uint32_t acc[16];
-        tmem_ld16(tlane + C_D2, acc);
-        float add[16];
-        ld_f32x16(add, s_f + F_B1);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-        relu_split16(acc, add, hi, lo, ovf);
-        tmem_st8(tlane + C_A3H, hi);
-        tmem_st8(tlane + C_A3L, lo);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(a_ready);
-        TC_STAMP(7);
-        if (valid) {
-          uint4* dst = a.es_out + (base + gt) * 4;
-          dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          if (a.logits != nullptr) {                                  // classifier 16 -> 8 -> 1 (fp32)
-            float hc[CH], wv[CH];
-            ld_f32x8(hc, s_f + F_CB0);
-#pragma unroll
-            for (int i = 0; i < DE; ++i) {
-              const float ei = fmaxf(__uint_as_float(acc[i]) + add[i], 0.f);
-              ld_f32x8(wv, s_f + F_CW0 + i * CH);
-#pragma unroll
-              for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, wv[o], hc[o]);
-            }
-            ld_f32x8(wv, s_f + F_CW1);
-            float lg = s_f[F_CB1];
-#pragma unroll
-            for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), wv[o], lg);
-            a.logits[a.slot_edge[base + gt]] = lg;
-          }
-        }
-      }
-      // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand
-      {
-        TC_STAMP(8);
-        mbar_wait(d_ready, pd); pd ^= 1;
-        TC_STAMP(9);
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < FHP / 16; ++ch) {
-          uint32_t acc[16];
-          tmem_ld16(tlane + C_D3 + 16 * ch, acc);
-          float add[16];
-          ld_f32x16(add, s_f + F_FB0 + 16 * ch);
-          tc_wait_ld();
-          uint32_t hi[8], lo[8];
-          relu_split16(acc, add, hi, lo, ovf);
-          tmem_st8(tlane + C_A4H + 8 * ch, hi);
-          tmem_st8(tlane + C_A4L + 8 * ch, lo);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(a_ready);
-        TC_STAMP(10);
-      }
-      // ---- epilogue 4: m = ReLU(D4 + fb1); per-row sums over this warp's 32 slots, in slot order
-      {
-        mbar_wait(d_ready, pd); pd ^= 1;
-        TC_STAMP(11);
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < DN / 16; ++ch) {
-          uint32_t acc[16];
-          tmem_ld16(tlane + C_D4 + 16 * ch, acc);
-          float add[16];
-          ld_f32x16(add, s_f + F_FB1 + 16 * ch);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
-            s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (cw > 0) {                                                 // warp-uniform
-          const int f = lane;                                         // lane = feature from here on
-          const int dir_off = dir_out ? DN : 0;                       // cat(flow_in, flow_out), mpn.py:97
-          const int64_t chunk_id = chunk_off + (cs - seg_base) / CHUNK;
-          const int32_t r_prev = __shfl_sync(0xffffffffu, nb, 0);
-          const int32_t r_next = __shfl_sync(0xffffffffu, nb, 31);
-          const int32_t r_after = __shfl_down_sync(0xffffffffu, r, 1);
-          const bool seg_end_here = lane < cw && (lane == cw - 1 || r_after != r);
-          unsigned ends = __ballot_sync(0xffffffffu, seg_end_here);     // bit q: slot q closes a row segment
-          int s0 = 0;
-          while (ends) {                                               // warp-uniform
-            const int e1 = __ffs(ends) - 1;
-            ends &= ends - 1;
-            const int32_t cur = __shfl_sync(0xffffffffu, r, e1);
-            float sum = 0.f;
-            for (int q = s0; q <= e1; ++q) sum += s_msg[q * MSG_LD + f];
-            const bool starts_before = s0 == 0 && r_prev == cur;
-            const bool continues = e1 == cw - 1 && r_next == cur;
-            if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
-            else a.part[(chunk_id * 2 + (s0 == 0 ? 0 : 1)) * DN + f] = sum;
-            s0 = e1 + 1;
-          }
-        }
-        __syncwarp();
-        TC_STAMP(12);
-        ++trace_i;
-      }
-      p = pn; have = have_n; base = base_n; cnt = cnt_n; slot = slot_n; r = rn; c = cn;
-    }
-    if (ovf & 0x80008000u) atomicOr(a.status, 1);
-  } else {
-    // ================================================================ MMA issuer (warp 8, one elected lane issues)
-    // The whole warp runs the (uniform) scheduling loop so that every MMA operand lives in a uniform
-    // register; only the tcgen05.mma / commit instructions are predicated on the elected lane.
-    // Serves whichever group has its next layer's operands ready (no head-of-line blocking), so the
-    // two tiles in flight drift apart and one group's epilogue overlaps the other's MMAs.
-    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
-    const uint64_t dbase = smem_desc_kmajor(smem_u32(smem), 128, 256);  // + (byte offset >> 4) per slab
-    const uint32_t id80 = idesc_f16(128, EH), id16 = idesc_f16(128, DE), id64 = idesc_f16(128, FHP),
-                   id32 = idesc_f16(128, DN);
-    auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
-      const uint64_t dh = dbase + (uint64_t)(off_h >> 4), dl = dbase + (uint64_t)(off_l >> 4);
-      if (elect_one()) {
-        mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
-        mma_ts(d, ah, dl, idesc, 1u);
-        mma_ts(d, al, dh, idesc, 1u);
-      }
-    };
-    int pg[2] = {cta_in_dir, cta_in_dir};          // pair index each group works on
-    int layer[2] = {1, 1};
-    uint32_t pa[2] = {0, 0};
-    bool live[2] = {2 * pg[0] + 0 < tiles_dir, 2 * pg[1] + 1 < tiles_dir};
-    int g = 0;
-    while (live[0] || live[1]) {
-      const bool ready = live[g] && __shfl_sync(0xffffffffu, (int)mbar_test(&bars[g], pa[g]), 0) != 0;
-      if (!ready) { g ^= 1; continue; }
-      pa[g] ^= 1;
-      tc_fence_after();
-      const uint32_t cb = tb + (uint32_t)g * 256u;
-      if (layer[g] == 1) {
+  // ---- MMA issue: run by the group's warp 0 (all lanes, uniform operands), one elected lane issues.
+  const uint64_t dbase = smem_desc_kmajor(smem_u32(smem), 128, 256);   // + (byte offset >> 4) per slab
+  auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+    const uint64_t dh = dbase + (uint64_t)(off_h >> 4), dl = dbase + (uint64_t)(off_l >> 4);
+    mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
+    mma_ts(d, ah, dl, idesc, 1u);
+    mma_ts(d, al, dh, idesc, 1u);
+  };
+  auto issue_layer = [&](int layer) {
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t cb = tcol;
+      if (layer == 1) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           step3(cb + C_D1, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB,
-                id80, ks == 0);
+                idesc_f16(128, EH), ks == 0);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
           step3(cb + C_D1, cb + C_EH + 8 * ks, cb + C_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB,
-                OFF_L1L + (4 + ks) * L1_SLAB, id80, false);
-      } else if (layer[g] == 2) {
+                OFF_L1L + (4 + ks) * L1_SLAB, idesc_f16(128, EH), false);
+      } else if (layer == 2) {
 #pragma unroll
         for (int ks = 0; ks < L2_KS; ++ks)
-          step3(cb + C_D2, cb + C_A2H + 8 * ks, cb + C_A2L + 8 * ks, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
-                id16, ks == 0);
-      } else if (layer[g] == 3) {
+          step3(cb + C_D2, cb + C_A2 + 16 * ks, cb + C_A2 + 16 * ks + 8, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
+                idesc_f16(128, DE), ks == 0);
+      } else if (layer == 3) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           step3(cb + C_D3, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB,
-                id64, ks == 0);
-        step3(cb + C_D3, cb + C_A3H, cb + C_A3L, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, id64, false);
+                idesc_f16(128, FHP), ks == 0);
+        step3(cb + C_D3, cb + C_A3, cb + C_A3 + 8, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, idesc_f16(128, FHP),
+              false);
       } else {
 #pragma unroll
         for (int ks = 0; ks < L4_KS; ++ks)
-          step3(cb + C_D4, cb + C_A4H + 8 * ks, cb + C_A4L + 8 * ks, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
-                id32, ks == 0);
+          step3(cb + C_D4, cb + C_A4 + 16 * ks, cb + C_A4 + 16 * ks + 8, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
+                idesc_f16(128, DN), ks == 0);
       }
-      if (elect_one()) mma_commit(&bars[2 + g]);
-      __syncwarp();
-      if (++layer[g] == 5) {
-        layer[g] = 1;
-        pg[g] += ctas_in_dir;
-        live[g] = 2 * pg[g] + g < tiles_dir;
-      }
-      g ^= 1;
+      mma_commit(d_ready);
     }
+    __syncwarp();
+  };
+  // operands written to TMEM by all 128 threads of the group -> visible to the MMAs of `layer`
+  auto publish_and_issue = [&](int layer) {
+    tc_wait_st();
+    tc_fence_before();
+    named_barrier(1 + g, TS);
+    if (wq == 0) issue_layer(layer);
+  };
+
+  // Operands of the warp's 32 edges -> their staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at
+  // +128, e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole
+  // 128-B lines: 8 lanes x 16 B per node row, 4 lanes x 16 B per edge row.
+  auto prefetch = [&](int32_t c, int64_t chunk_slot0, int64_t last_slot) {
+    const int sub8 = lane >> 3, pc8 = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + sub8;
+      const int32_t cr = __shfl_sync(0xffffffffu, c, row);
+      cp_async16(stage_warp + row * STAGE_ROW + pc8 * 16, a.xi + (int64_t)cr * 8 + pc8);
+      cp_async16(stage_warp + row * STAGE_ROW + 128 + pc8 * 16, a.xl + (int64_t)cr * 8 + pc8);
+    }
+    const int sub4 = lane >> 2, pc4 = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = i * 8 + sub4;
+      int64_t sl = chunk_slot0 + row;
+      sl = sl < last_slot ? sl : last_slot;                            // clamp: loads stay in range
+      cp_async16(stage_warp + row * STAGE_ROW + 256 + pc4 * 16, a.ei + sl * 4 + pc4);
+      cp_async16(stage_warp + row * STAGE_ROW + 320 + pc4 * 16, a.es_in + sl * 4 + pc4);
+    }
+  };
+
+  // Per-tile indices are loaded two tiles ahead so that no load latency sits on the tile's chain.
+  struct TileIdx { int64_t base; int cnt; int32_t r, c, se, nb; bool have; };
+  auto load_idx = [&](int p) {
+    TileIdx t;
+    t.have = 2 * p + g < tiles_dir;
+    t.base = 0; t.cnt = 0; t.r = 0; t.c = 0; t.se = 0; t.nb = -1;
+    if (t.have) {
+      t.base = seg_base + (int64_t)(2 * p + g) * TS;
+      t.cnt = (int)(seg_end - t.base < TS ? seg_end - t.base : TS);
+      const int64_t slot = gt < t.cnt ? t.base + gt : t.base + t.cnt - 1;   // clamp: loads stay in range
+      t.r = a.slot_row[slot];
+      t.c = a.slot_col[slot];
+      if (a.logits != nullptr) t.se = a.slot_edge[slot];
+      // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
+      const int64_t cs = t.base + wq * CHUNK;
+      const int cw = t.cnt - wq * CHUNK;
+      if (lane == 0 && cw > 0 && cs > seg_base) t.nb = a.slot_row[cs - 1];
+      if (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end) t.nb = a.slot_row[cs + CHUNK];
+    }
+    return t;
+  };
+  // Row sums of one tile's messages (already in s_msg), this warp's 32 slots, in slot order.
+  auto row_sums = [&](const TileIdx& t) {
+    const int64_t cs = t.base + wq * CHUNK;
+    int cw = t.cnt - wq * CHUNK;
+    cw = cw < 0 ? 0 : (cw > CHUNK ? CHUNK : cw);
+    if (cw > 0) {                                                     // warp-uniform
+      const int f = lane;                                             // lane = feature from here on
+      const int64_t chunk_id = chunk_off + (cs - seg_base) / CHUNK;
+      const int32_t r_prev = __shfl_sync(0xffffffffu, t.nb, 0);
+      const int32_t r_next = __shfl_sync(0xffffffffu, t.nb, 31);
+      const int32_t r_after = __shfl_down_sync(0xffffffffu, t.r, 1);
+      const bool seg_end_here = lane < cw && (lane == cw - 1 || r_after != t.r);
+      unsigned ends = __ballot_sync(0xffffffffu, seg_end_here);       // bit q: slot q closes a row segment
+      int s0 = 0;
+      while (ends) {                                                  // warp-uniform
+        const int e1 = __ffs(ends) - 1;
+        ends &= ends - 1;
+        const int32_t cur = __shfl_sync(0xffffffffu, t.r, e1);
+        float sum = 0.f;
+        for (int q = s0; q <= e1; ++q) sum += s_msg[q * MSG_LD + f];
+        const bool starts_before = s0 == 0 && r_prev == cur;
+        const bool continues = e1 == cw - 1 && r_next == cur;
+        if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
+        else a.part[(chunk_id * 2 + (s0 == 0 ? 0 : 1)) * DN + f] = sum;
+        s0 = e1 + 1;
+      }
+    }
+    __syncwarp();
+  };
+
+  TileIdx cur = load_idx(cta_in_dir);
+  TileIdx nxt = load_idx(cta_in_dir + ctas_in_dir);
+  TileIdx prev;
+  prev.have = false; prev.base = 0; prev.cnt = 0; prev.r = 0; prev.c = 0; prev.se = 0; prev.nb = -1;
+  if (cur.have) prefetch(cur.c, cur.base + wq * CHUNK, cur.base + cur.cnt - 1);
+  int p = cta_in_dir;
+  int trace_i = 0;
+#define TC_STAMP(k) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && trace_i < 64) a.trace[trace_i * 16 + (k)] = clock64(); } while (0)
+  while (cur.have) {
+    const bool valid = gt < cur.cnt;
+    TC_STAMP(0);
+    // ---- load phase: staged operands -> TMEM, then layer 1
+    cp_async_wait_all();
+    __syncwarp();                                                     // rows were fetched by other lanes
+    TC_STAMP(1);
+    {
+      auto st2 = [&](int col, int j) {
+        const uint4 x = s_stage[j], y = s_stage[j + 1];
+        const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        tmem_st8(tlane + col, w8);
+      };
+      st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
+      st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
+      st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
+      st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
+      st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
+      st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
+    }
+    publish_and_issue(1);
+    TC_STAMP(2);
+    // ---- while layer 1 runs: operands of the next tile, indices of the one after, row sums of the previous
+    if (nxt.have) prefetch(nxt.c, nxt.base + wq * CHUNK, nxt.base + nxt.cnt - 1);
+    p += ctas_in_dir;
+    TileIdx nn = load_idx(p + ctas_in_dir);
+    if (prev.have) row_sums(prev);
+    TC_STAMP(3);
+
+    // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand (in place over D1)
+    {
+      float pr[EH];
+      const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)cur.r * EH);
+#pragma unroll
+      for (int j = 0; j < EH / 4; ++j) {
+        const float4 v = __ldg(prp + j);
+        pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
+      }
+      mbar_wait(d_ready, pd); pd ^= 1;
+      TC_STAMP(4);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < EH / 16; ++ch) {
+        uint32_t acc[16];
+        tmem_ld16(tlane + C_D1 + 16 * ch, acc);
+        tc_wait_ld();
+        uint32_t hi[8], lo[8];
+        relu_split16(acc, pr + 16 * ch, hi, lo, ovf);
+        tmem_st8(tlane + C_A2 + 16 * ch, hi);
+        tmem_st8(tlane + C_A2 + 16 * ch + 8, lo);
+      }
+      publish_and_issue(2);
+      TC_STAMP(5);
+    }
+    // ---- epilogue 2: e' = ReLU(D2 + b1) -> state, layer-3 operand (in place over D2), classifier
+    {
+      mbar_wait(d_ready, pd); pd ^= 1;
+      TC_STAMP(6);
+      tc_fence_after();
+      uint32_t acc[16];
+      tmem_ld16(tlane + C_D2, acc);
+      float add[16];
+      ld_f32x16(add, s_f + F_B1);
+      tc_wait_ld();
+      uint32_t hi[8], lo[8];
+      relu_split16(acc, add, hi, lo, ovf);
+      tmem_st8(tlane + C_A3, hi);
+      tmem_st8(tlane + C_A3 + 8, lo);
+      publish_and_issue(3);
+      TC_STAMP(7);
+      if (valid) {
+        uint4* dst = a.es_out + (cur.base + gt) * 4;
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        if (a.logits != nullptr) {                                    // classifier 16 -> 8 -> 1 (fp32)
+          float hc[CH], wv[CH];
+          ld_f32x8(hc, s_f + F_CB0);
+#pragma unroll
+          for (int i = 0; i < DE; ++i) {
+            const float ei = fmaxf(__uint_as_float(acc[i]) + add[i], 0.f);
+            ld_f32x8(wv, s_f + F_CW0 + i * CH);
+#pragma unroll
+            for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, wv[o], hc[o]);
+          }
+          ld_f32x8(wv, s_f + F_CW1);
+          float lg = s_f[F_CB1];
+#pragma unroll
+          for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), wv[o], lg);
+          a.logits[cur.se] = lg;
+        }
+      }
+    }
+    // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand (in place over D3)
+    {
+      TC_STAMP(8);
+      mbar_wait(d_ready, pd); pd ^= 1;
+      TC_STAMP(9);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < FHP / 16; ++ch) {
+        uint32_t acc[16];
+        tmem_ld16(tlane + C_D3 + 16 * ch, acc);
+        float add[16];
+        ld_f32x16(add, s_f + F_FB0 + 16 * ch);
+        tc_wait_ld();
+        uint32_t hi[8], lo[8];
+        relu_split16(acc, add, hi, lo, ovf);
+        tmem_st8(tlane + C_A4 + 16 * ch, hi);
+        tmem_st8(tlane + C_A4 + 16 * ch + 8, lo);
+      }
+      publish_and_issue(4);
+      TC_STAMP(10);
+    }
+    // ---- epilogue 4: m = ReLU(D4 + fb1) -> shared memory; its row sums run under the next tile's layer 1
+    {
+      mbar_wait(d_ready, pd); pd ^= 1;
+      TC_STAMP(11);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < DN / 16; ++ch) {
+        uint32_t acc[16];
+        tmem_ld16(tlane + C_D4 + 16 * ch, acc);
+        float add[16];
+        ld_f32x16(add, s_f + F_FB1 + 16 * ch);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
+          s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      TC_STAMP(12);
+      ++trace_i;
+    }
+    prev = cur; cur = nxt; nxt = nn;
   }
-  __syncwarp();
+  if (prev.have) row_sums(prev);
+  if (ovf & 0x80008000u) atomicOr(a.status, 1);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tbase);
+  if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
 long long* g_trace = nullptr;   // set by mpn_tc_set_trace (development only)
