@@ -17,11 +17,13 @@
 // 64 B = [hi(16) | lo(16)], so loads are plain copies into TMEM and the bytes per edge-update
 // stay at 200.
 //
-// Warp roles (256 threads, 1 CTA / SM): warps 0-3 = group 0, warps 4-7 = group 1; each group keeps
-// one tile in flight and owns 256 of the 512 TMEM columns.  After a group's 128 threads have
-// written a layer's operand, an elected lane of the group's first warp issues that layer's MMAs and
-// commits them to the group's mbarrier; while one group runs an epilogue the tensor core runs the
-// other group's layer.  Operand rows of the next tile are staged with cp.async during the current one.
+// Warp roles (512 threads, 1 CTA / SM): two groups of 8 warps; each group keeps one tile in flight
+// and owns 256 of the 512 TMEM columns.  Every edge row is served by two threads (halves A and B of
+// the group) that split the columns of each epilogue.  After the group's 256 threads have written a
+// layer's operand, an elected lane of the group's first warp issues that layer's MMAs and commits
+// them to the group's mbarrier; while one group runs an epilogue the tensor core runs the other
+// group's layer.  Operand rows of the next tile are staged with cp.async during the current one,
+// the per-row message sums of the previous tile run under the current tile's first layer.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -32,7 +34,7 @@ using namespace ptx;
 
 constexpr int TS = 128;
 constexpr int DN = 32, DE = 16, EH = 80, FH = 56, FHP = 64, CH = 8;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;
 
 // ---- shared-memory weight image (bytes). Slab = one K=16 step of a B operand: [n/8][k/8][n%8][8 halfs]
 constexpr int L1_KS = 6, L1_SLAB = EH * 32;
@@ -53,7 +55,7 @@ constexpr int IMG_BYTES = (OFF_F32 + F_COUNT * 4 + 127) / 128 * 128;
 constexpr int C_XCH = 0, C_XCL = 32;        // x[col] hi / lo            (K = 64)
 constexpr int C_EH = 64, C_EL = 80;         // [e_init | e] hi / lo      (K = 32)
 constexpr int C_D1 = 96, C_A2 = C_D1;       // layer-1 accumulator (80 cols) -> layer-2 operand (K = 80)
-constexpr int C_D2 = 64, C_A3 = C_D2;       // layer-2 accumulator (16 cols, over the dead E region) -> e' operand
+constexpr int C_D2 = 64, C_A3 = 80;         // layer-2 accumulator (16 cols) and e' operand (16 cols), over the dead E region
 constexpr int C_D3 = 176, C_A4 = C_D3;      // layer-3 accumulator (64 cols) -> layer-4 operand (K = 64)
 constexpr int C_D4 = 0;                     // layer-4 accumulator, 32 cols (over the dead x[col])
 
@@ -372,22 +374,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   const uint32_t tbase = *tmem_slot;
   const float* s_f = reinterpret_cast<const float*>(smem + OFF_F32);
 
-  // Two groups of 4 warps, one 128-edge tile in flight each; a group owns 256 TMEM columns.
-  const int g = warp >> 2;
+  // Two groups of 8 warps, one 128-edge tile in flight each; a group owns 256 TMEM columns.  Every
+  // edge (TMEM lane) is served by TWO threads: half A (warps 0-3 of the group) and half B (warps 4-7)
+  // split the columns of each epilogue, the operand loads and the bookkeeping.
+  const int g = warp >> 3;
+  const bool half_b = ((warp >> 2) & 1) != 0;
   const int wq = warp & 3;                                            // quarter of the tile = this warp's TMEM lanes
-  const int gt = tid & (TS - 1);
+  const int gt = wq * 32 + lane;                                      // edge row inside the tile
   const uint32_t tcol = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u;   // uniform: MMA operand base
   const uint32_t tlane = tcol + ((uint32_t)(wq * 32) << 16);
-  float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + warp * CHUNK * MSG_LD;
+  float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + (g * 4 + wq) * CHUNK * MSG_LD;
   const uint32_t stage_warp = smem_u32(smem + SM_STAGE + (g * TS + wq * CHUNK) * STAGE_ROW);
   const uint4* s_stage = reinterpret_cast<const uint4*>(smem + SM_STAGE + (g * TS + gt) * STAGE_ROW);
   uint64_t* d_ready = &bars[g];
   const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
   const int dir_off = dir_out ? DN : 0;                               // cat(flow_in, flow_out), mpn.py:97
   uint32_t pd = 0;
-  uint32_t ovf = 0;
+  __half2 vmax = __floats2half2_rn(0.f, 0.f);                         // running max of every hi word (overflow check)
 
-  // ---- MMA issue: run by the group's warp 0 (all lanes, uniform operands), one elected lane issues.
+  // ---- MMA issue: run by the group's first warp (all lanes, uniform operands), one elected lane issues.
   const uint64_t dbase = smem_desc_kmajor(smem_u32(smem), 128, 256);   // + (byte offset >> 4) per slab
   auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
     const uint64_t dh = dbase + (uint64_t)(off_h >> 4), dl = dbase + (uint64_t)(off_l >> 4);
@@ -430,18 +435,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
     }
     __syncwarp();
   };
-  // operands written to TMEM by all 128 threads of the group -> visible to the MMAs of `layer`
+  // operands written to TMEM by all 256 threads of the group -> visible to the MMAs of `layer`
   auto publish_and_issue = [&](int layer) {
     tc_wait_st();
     tc_fence_before();
-    named_barrier(1 + g, TS);
-    if (wq == 0) issue_layer(layer);
+    named_barrier(1 + g, 2 * TS);
+    if (!half_b && wq == 0) issue_layer(layer);
+  };
+  // one accumulator chunk (16 fp32 columns) -> + add -> ReLU -> fp16 hi/lo, written back in place
+  auto epilogue_chunk = [&](int col, const float* add) {
+    uint32_t acc[16];
+    tmem_ld16(tlane + col, acc);
+    tc_wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+      vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
+    }
+    tmem_st8(tlane + col, hi);
+    tmem_st8(tlane + col + 8, lo);
   };
 
-  // Operands of the warp's 32 edges -> their staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at
-  // +128, e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole
-  // 128-B lines: 8 lanes x 16 B per node row, 4 lanes x 16 B per edge row.
-  auto prefetch = [&](int32_t c, int64_t chunk_slot0, int64_t last_slot) {
+  // Operand rows of the warp's 32 edges -> staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at +128,
+  // e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole 128-B
+  // lines.  Half A fetches (and later stores to TMEM) the node rows, half B the edge rows.
+  auto prefetch_nodes = [&](int32_t c) {
     const int sub8 = lane >> 3, pc8 = lane & 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -450,6 +469,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
       cp_async16(stage_warp + row * STAGE_ROW + pc8 * 16, a.xi + (int64_t)cr * 8 + pc8);
       cp_async16(stage_warp + row * STAGE_ROW + 128 + pc8 * 16, a.xl + (int64_t)cr * 8 + pc8);
     }
+  };
+  auto prefetch_edges = [&](int64_t chunk_slot0, int64_t last_slot) {
     const int sub4 = lane >> 2, pc4 = lane & 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -462,27 +483,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   };
 
   // Per-tile indices are loaded two tiles ahead so that no load latency sits on the tile's chain.
-  struct TileIdx { int64_t base; int cnt; int32_t r, c, se, nb; bool have; };
+  struct TileIdx { int64_t base; int cnt; int32_t r, x, nb; bool have; };   // x: col (half A) / slot_edge (half B)
   auto load_idx = [&](int p) {
     TileIdx t;
     t.have = 2 * p + g < tiles_dir;
-    t.base = 0; t.cnt = 0; t.r = 0; t.c = 0; t.se = 0; t.nb = -1;
+    t.base = 0; t.cnt = 0; t.r = 0; t.x = 0; t.nb = -1;
     if (t.have) {
       t.base = seg_base + (int64_t)(2 * p + g) * TS;
       t.cnt = (int)(seg_end - t.base < TS ? seg_end - t.base : TS);
       const int64_t slot = gt < t.cnt ? t.base + gt : t.base + t.cnt - 1;   // clamp: loads stay in range
       t.r = a.slot_row[slot];
-      t.c = a.slot_col[slot];
-      if (a.logits != nullptr) t.se = a.slot_edge[slot];
-      // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
-      const int64_t cs = t.base + wq * CHUNK;
-      const int cw = t.cnt - wq * CHUNK;
-      if (lane == 0 && cw > 0 && cs > seg_base) t.nb = a.slot_row[cs - 1];
-      if (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end) t.nb = a.slot_row[cs + CHUNK];
+      if (!half_b) {
+        t.x = a.slot_col[slot];
+      } else {
+        if (a.logits != nullptr) t.x = a.slot_edge[slot];
+        // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
+        const int64_t cs = t.base + wq * CHUNK;
+        const int cw = t.cnt - wq * CHUNK;
+        if (lane == 0 && cw > 0 && cs > seg_base) t.nb = a.slot_row[cs - 1];
+        if (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end) t.nb = a.slot_row[cs + CHUNK];
+      }
     }
     return t;
   };
-  // Row sums of one tile's messages (already in s_msg), this warp's 32 slots, in slot order.
+  // Row sums of one tile's messages (in s_msg), this warp's 32 slots, in slot order (half B).
   auto row_sums = [&](const TileIdx& t) {
     const int64_t cs = t.base + wq * CHUNK;
     int cw = t.cnt - wq * CHUNK;
@@ -494,19 +518,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
       const int32_t r_next = __shfl_sync(0xffffffffu, t.nb, 31);
       const int32_t r_after = __shfl_down_sync(0xffffffffu, t.r, 1);
       const bool seg_end_here = lane < cw && (lane == cw - 1 || r_after != t.r);
-      unsigned ends = __ballot_sync(0xffffffffu, seg_end_here);       // bit q: slot q closes a row segment
-      int s0 = 0;
-      while (ends) {                                                  // warp-uniform
-        const int e1 = __ffs(ends) - 1;
-        ends &= ends - 1;
-        const int32_t cur = __shfl_sync(0xffffffffu, t.r, e1);
-        float sum = 0.f;
-        for (int q = s0; q <= e1; ++q) sum += s_msg[q * MSG_LD + f];
-        const bool starts_before = s0 == 0 && r_prev == cur;
-        const bool continues = e1 == cw - 1 && r_next == cur;
-        if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
-        else a.part[(chunk_id * 2 + (s0 == 0 ? 0 : 1)) * DN + f] = sum;
-        s0 = e1 + 1;
+      const unsigned ends = __ballot_sync(0xffffffffu, seg_end_here); // bit q: slot q closes a row segment
+      float mv[CHUNK];
+#pragma unroll
+      for (int q = 0; q < CHUNK; ++q) mv[q] = s_msg[q * MSG_LD + f];
+      float sum = 0.f;
+      bool first_seg = true;
+#pragma unroll
+      for (int q = 0; q < CHUNK; ++q) {
+        sum += mv[q];
+        if ((ends >> q) & 1u) {                                       // warp-uniform
+          const int32_t cur = __shfl_sync(0xffffffffu, t.r, q);
+          const bool starts_before = first_seg && r_prev == cur;
+          const bool continues = q == cw - 1 && r_next == cur;
+          if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
+          else a.part[(chunk_id * 2 + (first_seg ? 0 : 1)) * DN + f] = sum;
+          sum = 0.f;
+          first_seg = false;
+        }
       }
     }
     __syncwarp();
@@ -515,17 +544,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   TileIdx cur = load_idx(cta_in_dir);
   TileIdx nxt = load_idx(cta_in_dir + ctas_in_dir);
   TileIdx prev;
-  prev.have = false; prev.base = 0; prev.cnt = 0; prev.r = 0; prev.c = 0; prev.se = 0; prev.nb = -1;
-  if (cur.have) prefetch(cur.c, cur.base + wq * CHUNK, cur.base + cur.cnt - 1);
+  prev.have = false; prev.base = 0; prev.cnt = 0; prev.r = 0; prev.x = 0; prev.nb = -1;
+  if (cur.have) {
+    if (!half_b) prefetch_nodes(cur.x);
+    else prefetch_edges(cur.base + wq * CHUNK, cur.base + cur.cnt - 1);
+  }
   int p = cta_in_dir;
   int trace_i = 0;
 #define TC_STAMP(k) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && trace_i < 64) a.trace[trace_i * 16 + (k)] = clock64(); } while (0)
   while (cur.have) {
     const bool valid = gt < cur.cnt;
     TC_STAMP(0);
-    // ---- load phase: staged operands -> TMEM, then layer 1
+    // hoisted row term of epilogue 1, this half's columns (A: 0..47, B: 48..79); consumed after layer 1
+    float pr[48];
+    {
+      const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)cur.r * EH) + (half_b ? 12 : 0);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        if (half_b && j >= 8) break;
+        const float4 v = __ldg(prp + j);
+        pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
+      }
+    }
+    // ---- load phase: staged operands -> TMEM (A: node rows, B: edge rows), then layer 1
     cp_async_wait_all();
-    __syncwarp();                                                     // rows were fetched by other lanes
+    __syncwarp();                                                     // rows were fetched by other lanes of this warp
     TC_STAMP(1);
     {
       auto st2 = [&](int col, int j) {
@@ -533,70 +576,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
         tmem_st8(tlane + col, w8);
       };
-      st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
-      st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
-      st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
-      st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
-      st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
-      st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
+      if (!half_b) {
+        st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
+        st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
+        st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
+        st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
+      } else {
+        st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
+        st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
+      }
     }
     publish_and_issue(1);
     TC_STAMP(2);
     // ---- while layer 1 runs: operands of the next tile, indices of the one after, row sums of the previous
-    if (nxt.have) prefetch(nxt.c, nxt.base + wq * CHUNK, nxt.base + nxt.cnt - 1);
+    if (nxt.have) {
+      if (!half_b) prefetch_nodes(nxt.x);
+      else prefetch_edges(nxt.base + wq * CHUNK, nxt.base + nxt.cnt - 1);
+    }
     p += ctas_in_dir;
     TileIdx nn = load_idx(p + ctas_in_dir);
-    if (prev.have) row_sums(prev);
+    if (half_b && prev.have) row_sums(prev);
     TC_STAMP(3);
 
-    // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand (in place over D1)
-    {
-      float pr[EH];
-      const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)cur.r * EH);
+    // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand (A: chunks 0-2, B: chunks 3-4)
+    mbar_wait(d_ready, pd); pd ^= 1;
+    TC_STAMP(4);
+    tc_fence_after();
+    if (!half_b) {
 #pragma unroll
-      for (int j = 0; j < EH / 4; ++j) {
-        const float4 v = __ldg(prp + j);
-        pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
-      }
-      mbar_wait(d_ready, pd); pd ^= 1;
-      TC_STAMP(4);
-      tc_fence_after();
+      for (int ch = 0; ch < 3; ++ch) epilogue_chunk(C_D1 + 16 * ch, pr + 16 * ch);
+    } else {
 #pragma unroll
-      for (int ch = 0; ch < EH / 16; ++ch) {
-        uint32_t acc[16];
-        tmem_ld16(tlane + C_D1 + 16 * ch, acc);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-        relu_split16(acc, pr + 16 * ch, hi, lo, ovf);
-        tmem_st8(tlane + C_A2 + 16 * ch, hi);
-        tmem_st8(tlane + C_A2 + 16 * ch + 8, lo);
-      }
-      publish_and_issue(2);
-      TC_STAMP(5);
+      for (int ch = 0; ch < 2; ++ch) epilogue_chunk(C_D1 + 48 + 16 * ch, pr + 16 * ch);
     }
-    // ---- epilogue 2: e' = ReLU(D2 + b1) -> state, layer-3 operand (in place over D2), classifier
+    publish_and_issue(2);
+    TC_STAMP(5);
+
+    // ---- epilogue 2: e' = ReLU(D2 + b1). A: state + layer-3 operand; B: classifier
+    mbar_wait(d_ready, pd); pd ^= 1;
+    TC_STAMP(6);
+    tc_fence_after();
     {
-      mbar_wait(d_ready, pd); pd ^= 1;
-      TC_STAMP(6);
-      tc_fence_after();
       uint32_t acc[16];
       tmem_ld16(tlane + C_D2, acc);
       float add[16];
       ld_f32x16(add, s_f + F_B1);
       tc_wait_ld();
-      uint32_t hi[8], lo[8];
-      relu_split16(acc, add, hi, lo, ovf);
-      tmem_st8(tlane + C_A3, hi);
-      tmem_st8(tlane + C_A3 + 8, lo);
-      publish_and_issue(3);
-      TC_STAMP(7);
-      if (valid) {
-        uint4* dst = a.es_out + (cur.base + gt) * 4;
-        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        if (a.logits != nullptr) {                                    // classifier 16 -> 8 -> 1 (fp32)
+      if (!half_b) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+          vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
+        }
+        tmem_st8(tlane + C_A3, hi);
+        tmem_st8(tlane + C_A3 + 8, lo);
+        publish_and_issue(3);
+        TC_STAMP(7);
+        if (valid) {
+          uint4* dst = a.es_out + (cur.base + gt) * 4;
+          dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      } else {
+        // B only reads D2 (A writes the e' operand to its own columns); it still takes part in the group
+        // barrier that precedes layer 3.
+        publish_and_issue(3);
+        if (valid && a.logits != nullptr) {                            // classifier 16 -> 8 -> 1 (fp32)
           float hc[CH], wv[CH];
           ld_f32x8(hc, s_f + F_CB0);
 #pragma unroll
@@ -610,58 +658,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
           float lg = s_f[F_CB1];
 #pragma unroll
           for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), wv[o], lg);
-          a.logits[cur.se] = lg;
+          a.logits[cur.x] = lg;
         }
       }
     }
-    // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand (in place over D3)
-    {
-      TC_STAMP(8);
-      mbar_wait(d_ready, pd); pd ^= 1;
-      TC_STAMP(9);
-      tc_fence_after();
+    // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand (A: chunks 0-1, B: chunks 2-3)
+    TC_STAMP(8);
+    mbar_wait(d_ready, pd); pd ^= 1;
+    TC_STAMP(9);
+    tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < FHP / 16; ++ch) {
-        uint32_t acc[16];
-        tmem_ld16(tlane + C_D3 + 16 * ch, acc);
-        float add[16];
-        ld_f32x16(add, s_f + F_FB0 + 16 * ch);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-        relu_split16(acc, add, hi, lo, ovf);
-        tmem_st8(tlane + C_A4 + 16 * ch, hi);
-        tmem_st8(tlane + C_A4 + 16 * ch + 8, lo);
-      }
-      publish_and_issue(4);
-      TC_STAMP(10);
+    for (int q = 0; q < 2; ++q) {
+      const int ch = (half_b ? 2 : 0) + q;
+      float add[16];
+      ld_f32x16(add, s_f + F_FB0 + 16 * ch);
+      epilogue_chunk(C_D3 + 16 * ch, add);
     }
-    // ---- epilogue 4: m = ReLU(D4 + fb1) -> shared memory; its row sums run under the next tile's layer 1
+    publish_and_issue(4);
+    TC_STAMP(10);
+
+    // ---- epilogue 4: m = ReLU(D4 + fb1) -> shared memory (A: features 0-15, B: 16-31); the row sums
+    //      run under the next tile's layer 1
+    mbar_wait(d_ready, pd); pd ^= 1;
+    TC_STAMP(11);
+    tc_fence_after();
     {
-      mbar_wait(d_ready, pd); pd ^= 1;
-      TC_STAMP(11);
-      tc_fence_after();
+      const int ch = half_b ? 1 : 0;
+      uint32_t acc[16];
+      tmem_ld16(tlane + C_D4 + 16 * ch, acc);
+      float add[16];
+      ld_f32x16(add, s_f + F_FB1 + 16 * ch);
+      tc_wait_ld();
 #pragma unroll
-      for (int ch = 0; ch < DN / 16; ++ch) {
-        uint32_t acc[16];
-        tmem_ld16(tlane + C_D4 + 16 * ch, acc);
-        float add[16];
-        ld_f32x16(add, s_f + F_FB1 + 16 * ch);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
-          s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
+        s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
       }
-      tc_fence_before();
-      __syncwarp();
-      TC_STAMP(12);
-      ++trace_i;
     }
+    tc_fence_before();
+    TC_STAMP(12);
+    ++trace_i;
     prev = cur; cur = nxt; nxt = nn;
   }
-  if (prev.have) row_sums(prev);
-  if (ovf & 0x80008000u) atomicOr(a.status, 1);
+  if (prev.have) {                                                    // row sums of the group's last tile
+    named_barrier(1 + g, 2 * TS);
+    if (half_b) row_sums(prev);
+  }
+  {
+    // hi parts are truncated (rz), so a value beyond the fp16 range shows up as the largest finite
+    // fp16 (0x7BFF = 65504) or inf: flag both (conservative).
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&vmax);
+    if ((w & 0x7FFFu) >= 0x7BFFu || ((w >> 16) & 0x7FFFu) >= 0x7BFFu) atomicOr(a.status, 1);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tbase);

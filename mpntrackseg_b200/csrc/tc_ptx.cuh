@@ -134,5 +134,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ReLU fused into the split: hi = fp16_rz(max(v,0)) (truncation keeps lo >= 0), lo = fp16_rn(max(v - hi, 0)).
+__device__ __forceinline__ void split2_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+}
+
 }  // namespace ptx
 }  // namespace mpn
