@@ -15,9 +15,7 @@ Inputs are larger than L2 (node features x are [N,2048,8,4] fp32 = 590 MB per wi
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -119,55 +117,58 @@ def run_reference(a):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled through NVML from a background thread DURING the timed
+    region (an `nvidia-smi -lms` subprocess was found to slow the timed loop down through driver locks)."""
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period=0.05):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), 0, False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                       '-lms', '100', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            return
+        self.period = period
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                 'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.p is None:
+        if not self.ok:
             return None
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], 0, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.f:
-            parts = [p.strip() for p in ln.split(',')]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx = max(mx, float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        if not sm:
+        self._stop.set()
+        self.t.join(timeout=2)
+        if not self.samples:
             return None
-        sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        sm = sorted(self.samples)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(sm))
 
 
 # ------------------------------------------------------------------ this repo's arm
 def run_b200(a):
     import torch.distributed as dist
     from mpntrackseg_b200 import _cabi
-    from mpntrackseg_b200.data.mot_graph import MOTGraph
     from mpntrackseg_b200.models.mpn import MOTMPNet
 
     rank = int(os.environ.get('RANK', '0'))
@@ -199,20 +200,46 @@ def run_b200(a):
     fps = wins[0].fps
     h2d_bytes = sum(t.numel() * t.element_size() for h in host for t in h.values())
 
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+
     def step(inputs):
-        graphs = []
-        for d in inputs:
-            g = MOTGraph(d, d['reid'], d['x'], None, {'fps': fps}, ds).construct_graph_object()
-            graphs.append(g)
+        """One pass of the hot path over the GPU's windows: batched KNN graph build + edge features,
+        node / edge encoders, 12 MP steps + classifier (block-diagonal batch)."""
+        batch = build_window_graphs(inputs, ds, fps, device=dev)
         with torch.no_grad():
-            outs = model.forward_batch(graphs)
-        return graphs, outs
+            out = model.forward_batch(batch)
+        return batch, out
+
+    copy_stream = torch.cuda.Stream(device=dev)
 
     def step_e2e():
-        inputs = [{k: v.to(dev, non_blocking=True) for k, v in h.items()} for h in host]
-        graphs, outs = step(inputs)
-        res = [o['classified_edges'][-1].cpu() for o in outs]        # D2H of the result
-        return graphs, res
+        """Same through the public API from pinned host buffers: the small per-detection tables are
+        copied first, the big node-feature tensors follow on a copy stream and each window's encoder
+        waits only for its own x (H2D overlaps the graph build); logits are read back."""
+        main = torch.cuda.current_stream()
+        inputs, events = [], []
+        with torch.cuda.stream(copy_stream):
+            for h in host:
+                inputs.append({k: v.to(dev, non_blocking=True) for k, v in h.items() if k != 'x'})
+            small = torch.cuda.Event()
+            small.record(copy_stream)
+            for h, d in zip(host, inputs):
+                d['x'] = h['x'].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        main.wait_event(small)
+        batch = build_window_graphs(inputs, ds, fps, device=dev)
+        enc = []
+        with torch.no_grad():
+            for d, ev in zip(inputs, events):
+                main.wait_event(ev)
+                d['x'].record_stream(main)
+                enc.append(model.encode_nodes(d['x']))
+            batch.xs = torch.cat(enc)                                 # already encoded [N,32]
+            out = model.forward_batch(batch, encoded=True)
+        res = out.logits[-1].cpu()                                    # D2H of the result (last step's logits)
+        return batch, res
 
     def sync_all():
         torch.cuda.synchronize()
@@ -221,10 +248,10 @@ def run_b200(a):
             torch.cuda.synchronize()
 
     for _ in range(a.warmup):
-        graphs, _ = step(devin)
+        batch, _ = step(devin)
     torch.cuda.synchronize()
-    edges = sum(g.edge_index.shape[1] for g in graphs)
-    nodes = sum(g.x.shape[0] for g in graphs)
+    edges = batch.num_edges
+    nodes = batch.num_nodes
 
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local) if rank == 0 else None
@@ -255,7 +282,7 @@ def run_b200(a):
     d2h = 0
     for _ in range(a.steps):
         _, res = step_e2e()
-        d2h = sum(r.numel() * r.element_size() for r in res)
+        d2h = res.numel() * res.element_size()
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1)

@@ -101,6 +101,23 @@ int mpn_edge_feats_assemble(const int64_t* row, const int64_t* col, int64_t num_
                             float* edge_attr /*[2P, attr_dim]*/, int64_t* edge_index /*[2,2P]*/,
                             void* stream);
 
+/* Fused, batched edge construction for G independent windows (training-mode semantics of
+ * data/mot_graph.py:195-221 = get_time_valid_conn_ixs + F.pairwise_distance + get_knn_mask with
+ * symmetric_edges=False + boolean indexing), one host synchronisation in total.
+ *   node_graph_ptr [G+1] (device AND host copy): node range of each window; node ids are batch-global.
+ *   top_k < 0 keeps every time-valid pair (inference-mode graphs, data/mot_graph.py:209-210).
+ * Outputs: kept pairs (row<col) sorted by (row, col) with their ReID distance, and
+ * graph_pair_ptr [G+1] (device + host): pair range of each window.  capacity = size of the out arrays
+ * (sum over windows of N_g*min(k, N_g) is always enough); MPN_ENOSPC if exceeded.
+ * workspace: mpn_knn_graph_workspace(N, sum_g N_g^2, G) bytes (dense fp32 distance blocks). */
+int64_t mpn_knn_graph_workspace(int64_t num_nodes, int64_t sum_sq_nodes, int64_t num_graphs);
+int mpn_knn_graph_pairs(const int64_t* frame_num, const int64_t* node_graph_ptr,
+                        const int64_t* h_node_graph_ptr, int64_t num_graphs, const float* reid,
+                        int64_t dim, int64_t top_k, int reciprocal, int64_t max_frame_dist,
+                        void* workspace, int64_t capacity, int64_t* out_row, int64_t* out_col,
+                        float* out_dist, int64_t* graph_pair_ptr, int64_t* h_graph_pair_ptr,
+                        void* stream);
+
 /* ------------------------------------------------------------------ model: layout */
 
 /* Internal edge layout for the fused message-passing kernels ("slots"): directed edges

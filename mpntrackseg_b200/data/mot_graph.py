@@ -137,3 +137,64 @@ class MOTGraph(object):
             self.graph_obj.reid_emb_dists = torch.cat((dist, dist))
         self.graph_obj.to(dev)
         return self.graph_obj
+
+
+class GraphBatch(object):
+    """Block-diagonal batch of independent window graphs built in one pass (extension; the
+    reference builds one window per ``MOTGraph``).  Node / edge ids are batch-global:
+    ``edge_index = [all (i<j) pairs of all windows | the same pairs reversed]``; window ``g`` owns
+    nodes ``node_ptr[g]:node_ptr[g+1]`` and pairs ``pair_ptr[g]:pair_ptr[g+1]`` of each half."""
+
+    def __init__(self, xs, node_ptr, edge_index, edge_attr, pair_ptr, reid_emb_dists=None):
+        self.xs, self.node_ptr, self.pair_ptr = xs, list(node_ptr), list(pair_ptr)
+        self.edge_index, self.edge_attr, self.reid_emb_dists = edge_index, edge_attr, reid_emb_dists
+
+    @property
+    def num_graphs(self):
+        return len(self.node_ptr) - 1
+
+    @property
+    def num_nodes(self):
+        return self.node_ptr[-1]
+
+    @property
+    def num_edges(self):
+        return self.edge_index.size(1)
+
+    def graph(self, g):
+        """Window ``g`` as a reference-style ``Graph`` (local node ids, reference edge order)."""
+        a, b, p = self.pair_ptr[g], self.pair_ptr[g + 1], self.pair_ptr[-1]
+        ei = torch.cat((self.edge_index[:, a:b], self.edge_index[:, p + a:p + b]), dim=1) - self.node_ptr[g]
+        ea = torch.cat((self.edge_attr[a:b], self.edge_attr[p + a:p + b]), dim=0)
+        x = self.xs[g] if isinstance(self.xs, (list, tuple)) else self.xs[self.node_ptr[g]:self.node_ptr[g + 1]]
+        return Graph(x=x, x_ext=None, edge_attr=ea, edge_index=ei)
+
+
+def build_window_graphs(windows, dataset_params, fps, inference_mode=False, max_frame_dist=None, device=None):
+    """Edge construction + assembly (``MOTGraph._get_edge_ixs`` + ``construct_graph_object``,
+    reference: data/mot_graph.py:195-221, 283-316) for a list of windows at once, on the GPU, with one
+    host synchronisation.  Each window is a mapping with ``frame, bb_height, bb_width, feet_x, feet_y``
+    (arrays / tensors, rows sorted by (frame, detection id)), ``reid`` [n,256] and ``x`` (node features)."""
+    dev = device or torch.device('cuda')
+    node_ptr = [0]
+    for w in windows:
+        node_ptr.append(node_ptr[-1] + int(w['reid'].shape[0]))
+    cat = lambda name, dt: torch.cat([_col(w, name, dev).to(dt).view(-1) for w in windows])
+    frame = cat('frame', torch.int64)
+    reid = torch.cat([w['reid'].to(dev, torch.float32) for w in windows])
+    mfd = dataset_params['max_frame_dist'] if max_frame_dist is None else max_frame_dist
+    k = None if inference_mode else dataset_params['top_k_nns']
+    pairs, dist, pair_ptr = ops.knn_graph_pairs(frame, node_ptr, reid, k, dataset_params['reciprocal_k_nns'],
+                                                -1 if mfd == 'max' else int(mfd))
+    use = dataset_params['edge_feats_to_use']
+    with_dist = 'emb_dist' in use
+    attr, edge_index = ops.edge_feats_assemble(pairs, frame.float(), cat('bb_height', torch.float32),
+                                               cat('bb_width', torch.float32), cat('feet_x', torch.float32),
+                                               cat('feet_y', torch.float32), fps, dist if with_dist else None)
+    order = ('secs_time_dists', 'norm_feet_x_dists', 'norm_feet_y_dists', 'bb_height_dists', 'bb_width_dists')
+    wanted = [order.index(n) for n in use if n in order] + ([5] if with_dist else [])
+    if wanted != list(range(attr.shape[1])):
+        attr = attr[:, wanted].contiguous()
+    xs = [w['x'] if w['x'].is_cuda else w['x'].to(dev) for w in windows]
+    return GraphBatch(xs, node_ptr, edge_index, attr, pair_ptr,
+                      torch.cat((dist, dist)) if inference_mode else None)

@@ -134,6 +134,32 @@ class MLPGraphIndependent(nn.Module):
         return out_edge, out_node
 
 
+class BatchOutput(object):
+    """Result of ``MOTMPNet.forward_batch``."""
+
+    def __init__(self, logits, batch, spans):
+        self.logits, self.batch, self.spans = logits, batch, spans
+
+    def __len__(self):
+        return self.batch.num_graphs if self.batch is not None else len(self.spans)
+
+    def graph_logits(self, g):
+        """[num_class_steps, E_g] logits of window ``g`` in the reference's per-window edge order."""
+        if self.batch is None:
+            a, b = self.spans[g]
+            return self.logits[:, a:b]
+        pp = self.batch.pair_ptr
+        a, b, p = pp[g], pp[g + 1], pp[-1]
+        return torch.cat((self.logits[:, a:b], self.logits[:, p + a:p + b]), dim=1)
+
+    def graph_output(self, g):
+        lg = self.graph_logits(g)
+        return {'classified_edges': [lg[i].reshape(-1, 1) for i in range(lg.shape[0])], 'mask_predictions': []}
+
+    def __getitem__(self, g):
+        return self.graph_output(g)
+
+
 class MOTMPNet(nn.Module):
     """Encoder -> ``num_enc_steps`` shared-weight message-passing steps -> edge classifier.
 
@@ -192,33 +218,41 @@ class MOTMPNet(nn.Module):
         lins = self.encoder.edge_model.linears()
         return ops.edge_encoder(edge_attr, layout, [l.weight for l in lins], [l.bias for l in lins])
 
-    def forward_batch(self, graphs):
+    def forward_batch(self, graphs, encoded=False):
         """Extension (not in the reference): evaluate several independent window graphs as one
-        block-diagonal batch (what torch_geometric's DataLoader does with batch_size > 1):
-        nodes are encoded per graph, edge indices are offset by the cumulative node count, and
-        one message-passing run covers all of them.  Returns one output dict per graph."""
-        x0s, eis, eas, sizes, off = [], [], [], [], 0
-        for g in graphs:
-            x0 = self.encode_nodes(g.x)
-            x0s.append(x0)
-            eis.append(g.edge_index + off)
-            eas.append(g.edge_attr)
-            sizes.append((x0.shape[0], g.edge_index.shape[1]))
-            off += x0.shape[0]
-        x0 = torch.cat(x0s)
-        edge_index = torch.cat(eis, dim=1)
-        layout = ops.edge_layout(edge_index, off)
-        e0 = self.encode_edges(torch.cat(eas), layout)
+        block-diagonal batch (what torch_geometric's DataLoader does with batch_size > 1): nodes are
+        encoded per window, and one message-passing run covers all of them.  ``graphs`` is a
+        ``data.mot_graph.GraphBatch`` (built in one pass by ``build_window_graphs``) or a list of
+        ``Graph`` objects.  Returns a ``BatchOutput``: ``.logits`` [num_class_steps, E_total] in the
+        batch's edge order and ``.graph_output(g)`` = the reference-style dict of window ``g``."""
+        from ..data.mot_graph import GraphBatch
+        if isinstance(graphs, GraphBatch):
+            batch = graphs
+            xs = batch.xs if isinstance(batch.xs, (list, tuple)) else [batch.xs]
+            if encoded:                                              # caller already ran encode_nodes per window
+                x0 = xs[0] if len(xs) == 1 else torch.cat(xs)
+            else:
+                x0 = torch.cat([self.encode_nodes(x) for x in xs]) if len(xs) > 1 else self.encode_nodes(xs[0])
+            edge_index, edge_attr, n = batch.edge_index, batch.edge_attr, batch.num_nodes
+            spans = None
+        else:
+            x0s, eis, eas, spans, off, eo = [], [], [], [], 0, 0
+            for g in graphs:
+                x0 = self.encode_nodes(g.x)
+                x0s.append(x0)
+                eis.append(g.edge_index + off)
+                eas.append(g.edge_attr)
+                spans.append((eo, eo + g.edge_index.shape[1]))
+                off += x0.shape[0]
+                eo += g.edge_index.shape[1]
+            x0, edge_index, edge_attr, n, batch = torch.cat(x0s), torch.cat(eis, dim=1), torch.cat(eas), off, None
+        layout = ops.edge_layout(edge_index, n)
+        e0 = self.encode_edges(edge_attr, layout)
         cw, keep = self.core_weights()
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
         logits = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, engine=self.engine)
-        outs, eo = [], 0
-        for _, e in sizes:
-            outs.append({'classified_edges': [logits[i, eo:eo + e].view(-1, 1) for i in range(logits.shape[0])],
-                         'mask_predictions': []})
-            eo += e
         del keep
-        return outs
+        return BatchOutput(logits, batch, spans)
 
     def forward(self, data, return_state=False):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr

@@ -108,6 +108,37 @@ def edge_feats_assemble(pairs, frame_f32, bb_height, bb_width, feet_x, feet_y, f
     return attr, eidx
 
 
+def knn_graph_pairs(frame_num, node_graph_ptr_host, reid, top_k, reciprocal, max_frame_dist=-1):
+    """Batched edge construction: (pairs [2,P] int64 batch-global ids sorted by (row,col), dist [P],
+    graph_pair_ptr list[G+1]).  node_graph_ptr_host: python list / CPU tensor of G+1 node offsets.
+    data/mot_graph.py:195-221 for every window of the batch in one pass."""
+    f = _req(frame_num, torch.int64, 'frame_num')
+    reid = _req(reid, torch.float32, 'reid')
+    hp = [int(v) for v in node_graph_ptr_host]
+    g = len(hp) - 1
+    n = hp[-1]
+    if f.numel() != n or reid.shape[0] != n:
+        raise ValueError('frame_num / reid do not match node_graph_ptr')
+    k = -1 if top_k is None else int(top_k)
+    sizes = [hp[i + 1] - hp[i] for i in range(g)]
+    cap = sum(s * min(k, s) if k >= 0 else s * (s - 1) // 2 for s in sizes)
+    cap = max(cap, 1)
+    dev = f.device
+    h_ptr = (C.c_int64 * (g + 1))(*hp)
+    d_ptr = torch.tensor(hp, dtype=torch.int64, device=dev)
+    ws = _bytes(lib().mpn_knn_graph_workspace(n, sum(s * s for s in sizes), g), dev)
+    pairs = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    dist = torch.empty(cap, dtype=torch.float32, device=dev)
+    gpp = torch.empty(g + 1, dtype=torch.int64, device=dev)
+    h_gpp = (C.c_int64 * (g + 1))()
+    check(lib().mpn_knn_graph_pairs(ptr(f), ptr(d_ptr), h_ptr, g, ptr(reid), reid.shape[1], k, int(bool(reciprocal)),
+                                    int(max_frame_dist), ptr(ws), cap, ptr(pairs[0]), ptr(pairs[1]), ptr(dist), ptr(gpp),
+                                    h_gpp, stream_ptr()), 'knn_graph_pairs')
+    hg = list(h_gpp)
+    p = hg[-1]
+    return torch.stack((pairs[0, :p], pairs[1, :p])) if p != cap else pairs, dist[:p], hg
+
+
 # ------------------------------------------------------------------ layout
 @dataclass
 class Layout:

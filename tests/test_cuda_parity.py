@@ -342,3 +342,46 @@ def test_tc_engine_reports_fp16_overflow_and_auto_falls_back():
         with pytest.warns(UserWarning, match='fp16 range'):
             auto = make_model(c['mp'], P, 'auto')(data)['classified_edges'][-1]
     assert torch.equal(auto, ref)
+
+
+def test_batched_graph_build_and_forward_match_per_window_path():
+    """build_window_graphs + forward_batch (one pass, batch-global ids) == per-window MOTGraph + forward,
+    and both match the oracle's edge sets."""
+    from mpntrackseg_b200.data.mot_graph import MOTGraph, build_window_graphs
+    shapes = [(6, 9, 5), (5, 12, 7), (7, 6, 40), (4, 8, 3)]
+    wins = [synth.make_window(T=t, D=d, k=k, seed=30 + i) for i, (t, d, k) in enumerate(shapes)]
+    mp = default_graph_model_params(5, 4)
+    P = synth.make_params(mp, seed=4, gain=2.0, core_only=True)
+    model = make_model(mp, P, 'tc')
+    for recip, mfd in ((True, 'max'), (False, 2)):
+        ds = default_dataset_params(top_k_nns=6, frames_per_graph=7, reciprocal_k_nns=recip)
+        inputs = [dict(synth.det_columns(w), reid=w.reid, x=w.x) for w in wins]
+        batch = build_window_graphs(inputs, ds, fps=30.0, max_frame_dist=mfd)
+        assert batch.num_graphs == len(wins)
+        with torch.no_grad():
+            out = model.forward_batch(batch)
+        for g, w in enumerate(wins):
+            ref_g = graph_ref.build_graph(w.frame, w.reid, synth.det_columns(w), w.fps, ds, max_frame_dist=mfd)
+            gg = batch.graph(g)
+            assert torch.equal(gg.edge_index.cpu(), ref_g['edge_index']), (g, recip)
+            np.testing.assert_allclose(gg.edge_attr.cpu().numpy(), ref_g['edge_attr'].numpy(), rtol=3e-6, atol=1e-6)
+            single = MOTGraph(synth.det_columns(w), w.reid, w.x, None, {'fps': 30.0}, ds,
+                              max_frame_dist=mfd).construct_graph_object()
+            assert torch.equal(single.edge_index, gg.edge_index)
+            with torch.no_grad():
+                ref = mpn_ref.mpn_forward(P, mp, w.x, ref_g['edge_index'], ref_g['edge_attr'])
+            got = out.graph_logits(g).cpu().numpy()
+            exp = torch.stack([t.view(-1) for t in ref['classified_edges']]).numpy()
+            assert_logits_close(got, exp, f'batch graph {g}')
+            assert len(out[g]['classified_edges']) == 4
+
+
+def test_batched_builder_inference_mode_keeps_all_time_valid_pairs():
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    w = synth.make_window(T=6, D=7, k=5, seed=77)
+    ds = default_dataset_params(top_k_nns=5, frames_per_graph=4)
+    batch = build_window_graphs([dict(synth.det_columns(w), reid=w.reid, x=w.x)], ds, fps=30.0, inference_mode=True,
+                                max_frame_dist=3)
+    ref = graph_ref.build_graph(w.frame, w.reid, synth.det_columns(w), w.fps, ds, inference_mode=True, max_frame_dist=3)
+    assert torch.equal(batch.edge_index.cpu(), ref['edge_index'])
+    np.testing.assert_allclose(batch.reid_emb_dists.cpu().numpy(), ref['reid_emb_dists'].numpy(), rtol=3e-6)
