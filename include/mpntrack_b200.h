@@ -207,6 +207,13 @@ int mpn_mp_forward(const mpn_core_weights* h_w, const mpn_edge_layout* h_g,
                    int32_t first_class_step, void* workspace, float* logits,
                    float* x_out, float* e_out, void* stream);
 
+/* models/mpn.py:117-137  TimeAwareAttentionModel aggregation: per node, softmax of the edge logits over its
+ * future (row<col) resp. past (row>col) neighbours (scatter_softmax, eps 1e-12) and the weighted sum of
+ * the neighbours' feature maps z[col] ([N, feat], feat = C*H*W).  logits: [E] in the caller's edge
+ * order (one classified step).  flow_in / flow_out: [N, feat]; nodes without neighbours get zeros. */
+int mpn_attn_aggregate(const float* z, int64_t num_nodes, int64_t feat, const mpn_edge_layout* h_g,
+                       const float* logits, float* flow_in, float* flow_out, void* stream);
+
 /* Same contract as mpn_mp_forward (num_steps >= 1), evaluated on the tcgen05 tensor cores:
  * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).

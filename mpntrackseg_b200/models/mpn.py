@@ -13,6 +13,7 @@ from torch import nn
 
 from .. import ops
 from ..config import core_dims
+from .cnn import CNN, MaskRCNNPredictor
 from .mlp import MLP
 
 
@@ -111,6 +112,40 @@ class MetaLayer(nn.Module):
         return '{}(edge_model={}, node_model={})'.format(self.__class__.__name__, self.edge_model, self.node_model)
 
 
+class TimeAwareAttentionModel(nn.Module):
+    """Attentive aggregation of the node feature maps followed by the 3x3 conv stack.
+    ``forward(x, edge_index, edge_attr, cls_net)`` keeps the reference's signature; the fused path calls
+    ``aggregate`` with a precomputed slot layout and the step's logits.  reference: models/mpn.py:102-137"""
+
+    def __init__(self, node_model, flow_in_attention_model=None, flow_out_attention_model=None):
+        super().__init__()
+        self.node_model = node_model        # the two attention MLPs are built and dropped by the reference (:106-109)
+
+    def aggregate(self, x, layout, logits):
+        flow_in, flow_out = ops.attn_aggregate(x, layout, logits)
+        return self.node_model(torch.cat((x, flow_in, flow_out), dim=1))
+
+    def forward(self, x, edge_index, edge_attr, cls_net):
+        dec_edge_feats, _ = cls_net(edge_attr)
+        layout = ops.edge_layout(edge_index, x.shape[0])
+        return self.aggregate(x.contiguous(), layout, dec_edge_feats.reshape(-1)), dec_edge_feats
+
+
+class MaskModel(nn.Module):
+    """Mask head on cat[feature_encoder(x_ext), node embedding].  reference: models/mpn.py:180-206"""
+
+    def __init__(self, mask_model_params):
+        super().__init__()
+        self.feature_encoder = CNN(**mask_model_params['feature_encoder_feats_dict'])
+        self.layer_norm = nn.LayerNorm([64, 14, 14])
+        self.mask_head = CNN(**mask_model_params['mask_head_feats_dict'])
+        self.mask_predictor = MaskRCNNPredictor(**mask_model_params['mask_predictor_feats_dict'])
+
+    def forward(self, feature_embeds, node_embeds):
+        h = torch.cat((self.feature_encoder(feature_embeds), node_embeds), dim=1)
+        return self.mask_predictor(self.mask_head(self.layer_norm(h)))
+
+
 class MLPGraphIndependent(nn.Module):
     """Independent node / edge MLPs (encoder, classifier).  reference: models/mpn.py:139-178"""
 
@@ -176,7 +211,15 @@ class MOTMPNet(nn.Module):
         enc = model_params['encoder_feats_dict']
         self.encoder = MLPGraphIndependent(**enc)
         self.classifier = MLPGraphIndependent(**model_params['classifier_feats_dict'])
+        # mask branch (cuDNN convolutions + the attentive-aggregation kernel); same module names and
+        # registration order as the reference so that its checkpoints load with strict=True
+        self.has_mask_branch = 'node_ext_encoder_feats_dict' in model_params
+        if self.has_mask_branch:
+            self.node_ext_encoder = CNN(**model_params['node_ext_encoder_feats_dict'])
+            self.mask_predictor = MaskModel(model_params['mask_model_feats_dict'])
         self.MPNet = self._build_core_MPNet(model_params=model_params, encoder_feats_dict=enc)
+        if self.has_mask_branch:
+            self.MPAttentionNet = self._build_attention_MPNet(model_params=model_params)
         self.num_enc_steps = model_params['num_enc_steps']
         self.num_class_steps = model_params['num_class_steps']
         # 'auto' | 'tc' | 'fp32' (None = $MPN_ENGINE or 'auto'), see ops.mp_forward
@@ -205,6 +248,12 @@ class MOTMPNet(nn.Module):
         return MetaLayer(edge_model=EdgeModel(edge_model=edge_model),
                          node_model=TimeAwareNodeModel(flow_in_model=flow_in_model, flow_out_model=flow_out_model,
                                                        node_model=node_model, node_agg_fn=agg))
+
+    def _build_attention_MPNet(self, model_params):
+        """reference: models/mpn.py:319-331 (the two attention MLPs it constructs are never used)"""
+        nx = model_params['node_ext_model_feats_dict']
+        in_dim = 3 * model_params['node_ext_encoder_feats_dict']['dims'][-1] * self.node_factor
+        return TimeAwareAttentionModel(node_model=CNN(input_dim=in_dim, **nx))
 
     # ------------------------------------------------------------------ forward
     def core_weights(self):
@@ -256,6 +305,7 @@ class MOTMPNet(nn.Module):
 
     def forward(self, data, return_state=False):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
+        x_ext = getattr(data, 'x_ext', None) if self.has_mask_branch else None
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError('backward through the CUDA kernels is not wired yet: call under '
                                       'torch.no_grad() (as MPNTracker does, tracker/mpn_tracker.py:122)')
@@ -264,12 +314,31 @@ class MOTMPNet(nn.Module):
         e0 = self.encode_edges(edge_attr, layout)
         cw, keep = self.core_weights()
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
-        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, want_state=return_state,
+        # the attention branch needs the logits of EVERY step (models/mpn.py:377), the output only the last ones
+        first_needed = 1 if x_ext is not None else first_class_step
+        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_needed, want_state=return_state,
                              engine=self.engine)
         logits = res[0] if return_state else res
-        out = {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])],
+        skip = max(first_class_step, 1) - max(first_needed, 1) if self.num_enc_steps > 0 else 0
+        out = {'classified_edges': [logits[i].view(-1, 1) for i in range(skip, logits.shape[0])],
                'mask_predictions': []}
+        if x_ext is not None:
+            out['mask_predictions'] = self._mask_branch(x_ext, layout, logits, first_class_step)
         if return_state:
             out['node_state'], out['edge_state_slots'], out['layout'] = res[1], res[2], layout
         del keep
         return out
+
+    def _mask_branch(self, x_ext, layout, logits, first_class_step):
+        """Attentive node-feature-map updates + mask head per classified step.
+        reference: models/mpn.py:356,360,369-385 (and :387-392 for num_enc_steps == 0)"""
+        z0 = self.node_ext_encoder(x_ext)
+        z, masks = z0, []
+        for step in range(1, self.num_enc_steps + 1):
+            zc = torch.cat((z0, z), dim=1).contiguous()                # reattach the initial encoding (:373)
+            z = self.MPAttentionNet.aggregate(zc, layout, logits[step - 1])
+            if step >= first_class_step:
+                masks.append(self.mask_predictor(x_ext, z))
+        if self.num_enc_steps == 0:
+            masks.append(self.mask_predictor(x_ext, z))
+        return masks

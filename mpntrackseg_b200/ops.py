@@ -318,3 +318,17 @@ def mp_step(cw, layout, x_init, x_lat, e_init, e_lat, mode=3, want_logits=False)
     check(lib().mpn_mp_step(C.byref(cw), C.byref(g), *[ptr(t) for t in args], int(mode), ptr(ws), ptr(e_out),
                             ptr(x_out), ptr(logits), stream_ptr()), 'mp_step')
     return e_out, x_out, logits
+
+
+def attn_aggregate(z, layout, logits):
+    """(flow_in, flow_out) of the attentive aggregation, each shaped like ``z`` [N, C, H, W].
+    models/mpn.py:117-134"""
+    z = _req(z, torch.float32, 'z')
+    lg = _req(logits.reshape(-1), torch.float32, 'logits')
+    n = z.shape[0]
+    feat = z[0].numel() if n else 0
+    fin, fout = torch.empty_like(z), torch.empty_like(z)
+    g = layout.c_struct()
+    check(lib().mpn_attn_aggregate(ptr(z), n, feat, C.byref(g), ptr(lg), ptr(fin), ptr(fout), stream_ptr()),
+          'attn_aggregate')
+    return fin, fout

@@ -43,13 +43,13 @@ def test_state_dict_contract():
     from mpntrackseg_b200.models.mpn import MOTMPNet
     mp = default_graph_model_params()
     sd = MOTMPNet(mp).state_dict()
-    shapes = param_shapes(mp, core_only=True)
-    assert list(sd) and set(sd) == set(shapes)
-    for k, v in sd.items():
-        assert tuple(v.shape) == tuple(shapes[k]), k
     full = param_shapes(mp)
+    assert list(sd) == list(full)                     # same keys in the reference's registration order
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(full[k]), k
+    core = param_shapes(mp, core_only=True)
     assert sum(int(torch.tensor(s).prod()) for s in full.values()) == 740966
-    assert sum(int(torch.tensor(s).prod()) for s in shapes.values()) == 296293
+    assert sum(int(torch.tensor(s).prod()) for s in core.values()) == 296293
 
 
 def test_cpu_tensors_are_rejected():

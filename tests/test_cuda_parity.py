@@ -39,8 +39,7 @@ def make_model(mp, P, engine=None):
     from mpntrackseg_b200.models.mpn import MOTMPNet
     model = MOTMPNet(mp).to(dev()).eval()
     model.engine = engine
-    core = {k: v for k, v in P.items() if k in model.state_dict()}
-    model.load_state_dict(core, strict=True)
+    model.load_state_dict(P, strict=len(P) == len(model.state_dict()))   # core-only dicts leave the mask branch as is
     return model
 
 
@@ -385,3 +384,43 @@ def test_batched_builder_inference_mode_keeps_all_time_valid_pairs():
     ref = graph_ref.build_graph(w.frame, w.reid, synth.det_columns(w), w.fps, ds, inference_mode=True, max_frame_dist=3)
     assert torch.equal(batch.edge_index.cpu(), ref['edge_index'])
     np.testing.assert_allclose(batch.reid_emb_dists.cpu().numpy(), ref['reid_emb_dists'].numpy(), rtol=3e-6)
+
+
+@pytest.mark.parametrize('name', ['tiny_full', 'config1'])
+def test_full_forward_with_mask_branch_matches_reference_golden(name):
+    """MOTMPNet.forward(data) with x_ext: attentive aggregation kernel + cuDNN convs against the
+    reference's own full forward (mask_predictions of the classified steps)."""
+    c = load_case(name)
+    win, gold = c['win'], c['gold']
+    model = make_model(c['mp'], c['P'], 'tc')
+    data = Data()
+    data.x, data.x_ext = win.x.to(dev()), win.x_ext.to(dev())
+    data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    data.edge_attr = torch.from_numpy(gold['edge_attr']).to(dev())
+    with torch.backends.cudnn.flags(allow_tf32=False), torch.no_grad():
+        out = model(data)
+    logits = torch.stack([t.view(-1) for t in out['classified_edges']]).cpu().numpy()
+    assert_logits_close(logits, gold['logits'], name)
+    assert len(out['mask_predictions']) == c['mp']['num_class_steps']
+    m = out['mask_predictions'][-1]
+    assert tuple(m.shape) == (win.N, 1, 56, 56)
+    np.testing.assert_allclose(m[:, 0, ::7, ::7].cpu().numpy(), gold['mask_last_sample'], rtol=2e-3, atol=2e-3)
+    means = np.array([float(t.double().mean()) for t in out['mask_predictions']])
+    np.testing.assert_allclose(means, gold['mask_step_means'], rtol=2e-3, atol=1e-4)
+
+
+def test_attn_aggregate_against_oracle_softmax():
+    from mpntrackseg_b200 import ops
+    c = load_case('tiny_nonrecip')
+    ei = torch.from_numpy(c['gold']['edge_index'].astype(np.int64))
+    n = c['win'].N
+    g = torch.Generator().manual_seed(8)
+    z = torch.randn(n, 6, 5, 5, generator=g)
+    logits = torch.randn(ei.shape[1], 1, generator=g) * 3
+    lay = ops.edge_layout(ei.to(dev()), n)
+    fin, fout = ops.attn_aggregate(z.to(dev()), lay, logits.to(dev()))
+    src, dst = ei
+    for name, sel, got in (('out', src < dst, fout), ('in', src > dst, fin)):
+        w = mpn_ref.segment_softmax(logits[sel], src[sel])
+        ref = mpn_ref.segment_add(z[dst[sel]] * w[:, :, None, None], src[sel], n)
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6, err_msg=name)
