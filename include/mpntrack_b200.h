@@ -142,6 +142,15 @@ int mpn_avgpool(const float* x, int64_t n, int64_t c, int64_t hw, float* out, vo
 int mpn_linear(const float* in, int64_t m, int64_t k, const float* w, const float* b,
                int64_t o, int relu, float* out, void* stream);
 
+/* models/mpn.py:355 encoder.node_model for the shipped widths K -> 128 -> 32 (K a multiple of 64) on the
+ * tcgen05 tensor cores: x [N,K] (already pooled) -> out [N,32] = ReLU(W1 ReLU(W0 x + b0) + b1), fp16
+ * hi/lo split operands, fp32 accumulation.  *status != 0: a value left the fp16 range, rerun with
+ * mpn_linear.  workspace: mpn_node_encoder_tc_workspace(K) bytes (packed weight image). */
+int64_t mpn_node_encoder_tc_workspace(int64_t k0);
+int mpn_node_encoder_tc(const float* x, int64_t n, int64_t k0, const float* w0, const float* b0,
+                        int64_t hidden, const float* w1, const float* b1, int64_t out_dim,
+                        void* workspace, float* out, int32_t* status, void* stream);
+
 /* out[r] = in[idx[r]] for rows of `width` floats (edge_attr[slot_edge] for non-default
  * encoder widths, where the fused edge encoder below does not apply). */
 int mpn_gather_rows(const float* in, const int32_t* idx, int64_t rows, int64_t width, float* out,

@@ -54,6 +54,8 @@ SIGNATURES = {
     'mpn_edge_layout_build': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_vp]),
     'mpn_avgpool': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     'mpn_linear': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp]),
+    'mpn_node_encoder_tc_workspace': (c_i64, [c_i64]),
+    'mpn_node_encoder_tc': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'mpn_gather_rows': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     'mpn_edge_encoder': (C.c_int, [c_vp, c_vp, c_i64, C.POINTER(c_i32), c_i32, C.POINTER(c_vp),
                                    C.POINTER(c_vp), c_vp, c_vp]),

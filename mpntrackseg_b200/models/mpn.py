@@ -261,7 +261,9 @@ class MOTMPNet(nn.Module):
 
     def encode_nodes(self, x):
         """Global average pool + node MLP.  reference: models/mpn.py:351-355"""
-        return self.encoder.node_model(ops.avgpool(x) if x.dim() > 2 else x)
+        pooled = ops.avgpool(x) if x.dim() > 2 else x
+        lins = self.encoder.node_model.linears()
+        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins], engine=self.engine)
 
     def encode_edges(self, edge_attr, layout):
         lins = self.encoder.edge_model.linears()

@@ -202,6 +202,34 @@ def linear(inp, weight, bias, relu):
     return out
 
 
+def node_encoder(x, weights, biases, engine=None):
+    """encoder.node_model on pooled features x [N, K].  The shipped K -> 128 -> 32 stack runs as one
+    tcgen05 kernel (engine 'tc' / 'auto'); other widths, engine 'fp32' and fp16-range overflow use the
+    fp32 Linear kernel chain.  models/mpn.py:355"""
+    engine = engine or default_engine()
+    x = _req(x, torch.float32, 'x')
+    ws_ = [_req(w, torch.float32, 'weight') for w in weights]
+    bs_ = [_req(b, torch.float32, 'bias') for b in biases]
+    n, k0 = x.shape
+    fits = (len(ws_) == 2 and ws_[0].shape[0] == 128 and ws_[1].shape[0] == 32 and k0 % 64 == 0 and k0 >= 64
+            and x.data_ptr() % 16 == 0)
+    if fits and engine in ('auto', 'tc') and n > 0:
+        out = torch.empty((n, 32), dtype=torch.float32, device=x.device)
+        ws = _bytes(lib().mpn_node_encoder_tc_workspace(k0), x.device)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        check(lib().mpn_node_encoder_tc(ptr(x), n, k0, ptr(ws_[0]), ptr(bs_[0]), 128, ptr(ws_[1]), ptr(bs_[1]), 32,
+                                        ptr(ws), ptr(out), ptr(status), stream_ptr()), 'node_encoder_tc')
+        if (engine == 'tc' and not STRICT_TC_STATUS) or int(status.item()) == 0:
+            return out
+        if engine == 'tc':
+            raise OverflowError('node_encoder_tc: a value left the fp16 range; use engine="fp32"')
+        warnings.warn('mpntrackseg_b200: node features outside the fp16 range, rerunning the encoder on the fp32 kernels')
+    h = x
+    for w, b in zip(ws_, bs_):
+        h = linear(h, w, b, relu=w.shape[0] != 1)
+    return h
+
+
 def gather_rows(inp, idx):
     inp = _req(inp, torch.float32, 'input')
     idx = _req(idx, torch.int32, 'idx')

@@ -424,3 +424,20 @@ def test_attn_aggregate_against_oracle_softmax():
         w = mpn_ref.segment_softmax(logits[sel], src[sel])
         ref = mpn_ref.segment_add(z[dst[sel]] * w[:, :, None, None], src[sel], n)
         np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6, err_msg=name)
+
+
+def test_node_encoder_tc_against_fp32():
+    from mpntrackseg_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    for n in (1, 127, 300, 2250):
+        x = torch.randn(n, 2048, generator=g).abs()
+        w0, b0 = torch.randn(128, 2048, generator=g) / 45, torch.randn(128, generator=g) * 0.1
+        w1, b1 = torch.randn(32, 128, generator=g) / 11, torch.randn(32, generator=g) * 0.1
+        ref = torch.relu(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(x.double(), w0.double(), b0.double())),
+                                                    w1.double(), b1.double())).float()
+        args = (x.to(dev()), [w0.to(dev()), w1.to(dev())], [b0.to(dev()), b1.to(dev())])
+        got_tc = ops.node_encoder(*args, engine='tc').cpu()
+        got_32 = ops.node_encoder(*args, engine='fp32').cpu()
+        scale = float(ref.abs().max())
+        assert float((got_32 - ref).abs().max()) <= 2e-5 * scale
+        assert float((got_tc - ref).abs().max()) <= 2e-5 * scale, n
