@@ -184,7 +184,7 @@ def run_b200(a):
     ds = default_dataset_params(top_k_nns=a.k, frames_per_graph=a.frames)
     mp, P = model_and_params()
     model = MOTMPNet(mp).to(dev).eval()
-    model.load_state_dict(P, strict=True)
+    model.load_state_dict(P, strict=False)      # core weights; the mask branch keeps its init
 
     wins = make_windows(a, rank)
     gen = torch.Generator(device=dev).manual_seed(rank)

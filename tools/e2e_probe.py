@@ -11,7 +11,7 @@ dev = torch.device('cuda')
 ds = default_dataset_params(50, 15)
 mp = default_graph_model_params(12, 11)
 P = synth.make_params(mp, seed=9, gain=1.25, core_only=True)
-model = MOTMPNet(mp).to(dev).eval(); model.load_state_dict(P)
+model = MOTMPNet(mp).to(dev).eval(); model.load_state_dict(P, strict=False)
 G = 4
 wins = [synth.make_window(T=15, D=150, k=50, seed=g, node_dim=8) for g in range(G)]
 host = []

@@ -10,7 +10,7 @@ dev = torch.device('cuda')
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ds = default_dataset_params(50, 15); mp = default_graph_model_params(12, 11)
 P = synth.make_params(mp, seed=9, gain=1.25, core_only=True)
-model = MOTMPNet(mp).to(dev).eval(); model.load_state_dict(P); model.engine = 'tc'
+model = MOTMPNet(mp).to(dev).eval(); model.load_state_dict(P, strict=False); model.engine = 'tc'
 graphs = []
 for g in range(G):
     w = synth.make_window(T=15, D=150, k=50, seed=g)
