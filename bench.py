@@ -231,14 +231,16 @@ def run_b200(a):
         main.wait_event(small)
         batch = build_window_graphs(inputs, ds, fps, device=dev)
         enc = []
+        flags = torch.zeros(len(inputs), dtype=torch.int32, device=dev)
         with torch.no_grad():
-            for d, ev in zip(inputs, events):
+            for i, (d, ev) in enumerate(zip(inputs, events)):
                 main.wait_event(ev)
                 d['x'].record_stream(main)
-                enc.append(model.encode_nodes(d['x']))
+                enc.append(model.encode_nodes(d['x'], status=flags[i:i + 1]))
             batch.xs = torch.cat(enc)                                 # already encoded [N,32]
             out = model.forward_batch(batch, encoded=True)
         res = out.logits[-1].cpu()                                    # D2H of the result (last step's logits)
+        assert not flags.any().item(), 'fp16 overflow in the encoder (would need the fp32 rerun)'
         return batch, res
 
     def sync_all():

@@ -259,11 +259,27 @@ class MOTMPNet(nn.Module):
     def core_weights(self):
         return self.MPNet._weights(self.classifier.edge_model)
 
-    def encode_nodes(self, x):
-        """Global average pool + node MLP.  reference: models/mpn.py:351-355"""
-        pooled = ops.avgpool(x) if x.dim() > 2 else x
+    def encode_nodes(self, x, status=None):
+        """Global average pool + node MLP.  reference: models/mpn.py:351-355
+        status: optional int32[1] device tensor receiving the fp16-overflow flag of the tensor-core
+        encoder instead of a host sync + fallback here."""
+        return self.encode_nodes_list([x], status=status)
+
+    def encode_nodes_list(self, xs, engine=None, status=None):
+        """Node encoder over several windows' features in ONE kernel launch: every window is pooled into
+        its slice of a [N_total, C] buffer, then the whole buffer goes through the MLP."""
+        engine = engine or self.engine
+        if len(xs) == 1 and xs[0].dim() == 2:
+            pooled = xs[0]
+        else:
+            n_tot = sum(int(x.shape[0]) for x in xs)
+            pooled = torch.empty((n_tot, xs[0].shape[1]), dtype=torch.float32, device=xs[0].device)
+            off = 0
+            for x in xs:
+                ops.avgpool(x if x.dim() > 2 else x[:, :, None, None], out=pooled[off:off + x.shape[0]])
+                off += x.shape[0]
         lins = self.encoder.node_model.linears()
-        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins], engine=self.engine)
+        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins], engine=engine, status=status)
 
     def encode_edges(self, edge_attr, layout):
         lins = self.encoder.edge_model.linears()
@@ -279,30 +295,22 @@ class MOTMPNet(nn.Module):
         from ..data.mot_graph import GraphBatch
         if isinstance(graphs, GraphBatch):
             batch = graphs
-            xs = batch.xs if isinstance(batch.xs, (list, tuple)) else [batch.xs]
-            if encoded:                                              # caller already ran encode_nodes per window
-                x0 = xs[0] if len(xs) == 1 else torch.cat(xs)
-            else:
-                x0 = torch.cat([self.encode_nodes(x) for x in xs]) if len(xs) > 1 else self.encode_nodes(xs[0])
+            xs = list(batch.xs) if isinstance(batch.xs, (list, tuple)) else [batch.xs]
             edge_index, edge_attr, n = batch.edge_index, batch.edge_attr, batch.num_nodes
             spans = None
         else:
-            x0s, eis, eas, spans, off, eo = [], [], [], [], 0, 0
+            xs, eis, eas, spans, off, eo = [], [], [], [], 0, 0
             for g in graphs:
-                x0 = self.encode_nodes(g.x)
-                x0s.append(x0)
+                xs.append(g.x)
                 eis.append(g.edge_index + off)
                 eas.append(g.edge_attr)
                 spans.append((eo, eo + g.edge_index.shape[1]))
-                off += x0.shape[0]
+                off += g.x.shape[0]
                 eo += g.edge_index.shape[1]
-            x0, edge_index, edge_attr, n, batch = torch.cat(x0s), torch.cat(eis, dim=1), torch.cat(eas), off, None
+            edge_index, edge_attr, n, batch = torch.cat(eis, dim=1), torch.cat(eas), off, None
         layout = ops.edge_layout(edge_index, n)
-        e0 = self.encode_edges(edge_attr, layout)
-        cw, keep = self.core_weights()
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
-        logits = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_class_step, engine=self.engine)
-        del keep
+        logits = self._core(xs, edge_attr, layout, first_class_step, encoded=encoded)[0]
         return BatchOutput(logits, batch, spans)
 
     def forward(self, data, return_state=False):
@@ -311,16 +319,12 @@ class MOTMPNet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError('backward through the CUDA kernels is not wired yet: call under '
                                       'torch.no_grad() (as MPNTracker does, tracker/mpn_tracker.py:122)')
-        x0 = self.encode_nodes(x)
-        layout = ops.edge_layout(edge_index, x0.shape[0])
-        e0 = self.encode_edges(edge_attr, layout)
-        cw, keep = self.core_weights()
+        layout = ops.edge_layout(edge_index, x.shape[0])
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
         # the attention branch needs the logits of EVERY step (models/mpn.py:377), the output only the last ones
         first_needed = 1 if x_ext is not None else first_class_step
-        res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_needed, want_state=return_state,
-                             engine=self.engine)
-        logits = res[0] if return_state else res
+        res = self._core([x], edge_attr, layout, first_needed, want_state=return_state)
+        logits = res[0]
         skip = max(first_class_step, 1) - max(first_needed, 1) if self.num_enc_steps > 0 else 0
         out = {'classified_edges': [logits[i].view(-1, 1) for i in range(skip, logits.shape[0])],
                'mask_predictions': []}
@@ -328,8 +332,34 @@ class MOTMPNet(nn.Module):
             out['mask_predictions'] = self._mask_branch(x_ext, layout, logits, first_class_step)
         if return_state:
             out['node_state'], out['edge_state_slots'], out['layout'] = res[1], res[2], layout
-        del keep
         return out
+
+    def _core(self, xs, edge_attr, layout, first_needed, want_state=False, encoded=False):
+        """Encoders + step loop.  The tensor-core kernels report fp16-range overflow through one status
+        word that is read once at the end (a single host sync); 'auto' then reruns on the fp32 kernels."""
+        engine = self.engine or ops.default_engine()
+        cw, keep = self.core_weights()
+        for eng in ((engine,) if engine != 'auto' else ('auto', 'fp32')):
+            status = torch.zeros(2, dtype=torch.int32, device=edge_attr.device) if eng != 'fp32' else None
+            if encoded:
+                x0 = xs[0] if len(xs) == 1 else torch.cat(xs)
+            else:
+                x0 = self.encode_nodes_list(xs, engine=eng, status=None if status is None else status[0:1])
+            e0 = self.encode_edges(edge_attr, layout)
+            res = ops.mp_forward(cw, layout, x0, e0, self.num_enc_steps, first_needed, want_state=want_state,
+                                 engine=eng, status=None if status is None else status[1:2])
+            res = res if want_state else (res,)
+            if status is None or not (ops.STRICT_TC_STATUS or eng == 'auto'):
+                break
+            flags = status.tolist()                                    # the one host sync
+            if not any(flags):
+                break
+            if eng == 'tc':
+                raise OverflowError('a value left the fp16 range on the tensor-core path; use engine="fp32"')
+            import warnings
+            warnings.warn('mpntrackseg_b200: value outside the fp16 range, rerunning the forward on the fp32 kernels')
+        del keep
+        return res
 
     def _mask_branch(self, x_ext, layout, logits, first_class_step):
         """Attentive node-feature-map updates + mask head per classified step.

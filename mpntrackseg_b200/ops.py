@@ -174,16 +174,22 @@ def edge_layout(edge_index, num_nodes):
 
 
 # ------------------------------------------------------------------ encoders
-def avgpool(x):
-    """[N, C, H, W] -> [N, C].  models/mpn.py:351-352"""
+def avgpool(x, out=None):
+    """[N, C, H, W] -> [N, C] (optionally into a preallocated contiguous ``out``).  models/mpn.py:351-352"""
     x = _req(x, torch.float32, 'x')
     n, c = x.shape[0], x.shape[1]
     hw = 1
     for s in x.shape[2:]:
         hw *= s
     if hw == 1:
-        return x.reshape(n, c)
-    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        if out is None:
+            return x.reshape(n, c)
+        out.copy_(x.reshape(n, c))
+        return out
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    elif not (out.is_contiguous() and tuple(out.shape) == (n, c) and out.dtype == torch.float32):
+        raise ValueError('avgpool: out must be a contiguous fp32 [N, C] tensor')
     check(lib().mpn_avgpool(ptr(x), n, c, hw, ptr(out), stream_ptr()), 'avgpool')
     return out
 
@@ -202,10 +208,12 @@ def linear(inp, weight, bias, relu):
     return out
 
 
-def node_encoder(x, weights, biases, engine=None):
+def node_encoder(x, weights, biases, engine=None, status=None):
     """encoder.node_model on pooled features x [N, K].  The shipped K -> 128 -> 32 stack runs as one
     tcgen05 kernel (engine 'tc' / 'auto'); other widths, engine 'fp32' and fp16-range overflow use the
-    fp32 Linear kernel chain.  models/mpn.py:355"""
+    fp32 Linear kernel chain.  models/mpn.py:355
+    status: optional int32[1] device tensor; if given the overflow flag is left there for the caller to
+    check (no host sync here) and no fallback is attempted."""
     engine = engine or default_engine()
     x = _req(x, torch.float32, 'x')
     ws_ = [_req(w, torch.float32, 'weight') for w in weights]
@@ -216,10 +224,12 @@ def node_encoder(x, weights, biases, engine=None):
     if fits and engine in ('auto', 'tc') and n > 0:
         out = torch.empty((n, 32), dtype=torch.float32, device=x.device)
         ws = _bytes(lib().mpn_node_encoder_tc_workspace(k0), x.device)
-        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        deferred = status is not None
+        if status is None:
+            status = torch.zeros(1, dtype=torch.int32, device=x.device)
         check(lib().mpn_node_encoder_tc(ptr(x), n, k0, ptr(ws_[0]), ptr(bs_[0]), 128, ptr(ws_[1]), ptr(bs_[1]), 32,
                                         ptr(ws), ptr(out), ptr(status), stream_ptr()), 'node_encoder_tc')
-        if (engine == 'tc' and not STRICT_TC_STATUS) or int(status.item()) == 0:
+        if deferred or (engine == 'tc' and not STRICT_TC_STATUS) or int(status.item()) == 0:
             return out
         if engine == 'tc':
             raise OverflowError('node_encoder_tc: a value left the fp16 range; use engine="fp32"')
@@ -294,13 +304,15 @@ def default_engine():
     return eng
 
 
-def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False, engine=None):
+def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False, engine=None,
+               status=None):
     """Run the step loop.  Returns logits [S, E] (original edge order) and, if asked, the final
     node / edge latent states (edge state in slot order).  models/mpn.py:364-389
 
     engine: 'tc' = tcgen05 tensor-core kernels (fp16 hi/lo split operands, fp32 accumulate),
     'fp32' = fp32 SIMT kernels, 'auto' (default) = 'tc', rerun on 'fp32' if an activation left
-    the fp16 range."""
+    the fp16 range.  status: optional int32[1] device tensor: the overflow flag is left there for the
+    caller (no host sync, no fallback here)."""
     engine = engine or default_engine()
     x_init = _req(x_init, torch.float32, 'x_init')
     e_init = _req(e_init, torch.float32, 'e_init')
@@ -315,11 +327,13 @@ def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_sta
     use_tc = engine in ('auto', 'tc') and num_steps >= 1 and n > 0
     if use_tc:
         ws = _bytes(lib().mpn_mp_tc_workspace(n, e), dev)
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        deferred = status is not None
+        if status is None:
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
         check(lib().mpn_mp_forward_tc(C.byref(cw), C.byref(g), ptr(x_init), ptr(e_init), int(num_steps), int(first),
                                       ptr(ws), ptr(logits), ptr(x_out), ptr(e_out), ptr(status), stream_ptr()),
               'mp_forward_tc')
-        if engine == 'tc' and not STRICT_TC_STATUS:
+        if deferred or (engine == 'tc' and not STRICT_TC_STATUS):
             return (logits, x_out, e_out) if want_state else logits
         if int(status.item()) == 0:
             return (logits, x_out, e_out) if want_state else logits
