@@ -53,10 +53,13 @@ def workload_name(a):
             f'{feats}, full forward incl. ReID-distance KNN build; {a.graphs} windows per GPU per step')
 
 
-def make_windows(a, rank, device=None):
+def make_windows(a, rank, world):
+    """This rank's slice of the job's world*graphs windows (weak scaling: --graphs per GPU)."""
+    from mpntrackseg_b200.sharding import shard_range
+    lo, hi = shard_range(a.graphs * world, rank, world)
     wins = []
-    for g in range(a.graphs):
-        w = synth.make_window(T=a.frames, D=a.dets, k=a.k, seed=1000 * rank + g, node_feats='pooled', node_dim=8)
+    for g in range(lo, hi):
+        w = synth.make_window(T=a.frames, D=a.dets, k=a.k, seed=g, node_feats='pooled', node_dim=8)
         wins.append(w)
     return wins
 
@@ -186,7 +189,7 @@ def run_b200(a):
     model = MOTMPNet(mp).to(dev).eval()
     model.load_state_dict(P, strict=False)      # core weights; the mask branch keeps its init
 
-    wins = make_windows(a, rank)
+    wins = make_windows(a, rank, world)
     gen = torch.Generator(device=dev).manual_seed(rank)
     host, devin = [], []
     for w in wins:
@@ -289,13 +292,9 @@ def run_b200(a):
     sync_all()
     ms_e2e = t0.elapsed_time(t1)
 
-    tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    tot = torch.tensor([edges, nodes], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(tt[0]), float(tt[1])
-    all_edges = float(tot[0])
+    from mpntrackseg_b200.sharding import reduce_step_stats
+    ms, (all_edges, all_nodes, h2d_total, d2h_total) = reduce_step_stats(ms, [edges, nodes, h2d_bytes, d2h], device=dev)
+    ms_e2e, _ = reduce_step_stats(ms_e2e, [0], device=dev)
 
     if rank == 0:
         peaks = {}
@@ -322,7 +321,7 @@ def run_b200(a):
                     'edges_per_gpu': edges, 'nodes_per_gpu': nodes},
             graphs_per_s=a.graphs * world * a.steps / (ms * 1e-3),
             e2e=dict(value=NUM_STEPS_MP * all_edges * a.steps / (ms_e2e * 1e-3), unit=UNIT,
-                     h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h,
+                     h2d_bytes_per_step=int(h2d_total), d2h_bytes_per_step=int(d2h_total),
                      graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3)),
             gpu_launches=int(launches),
             roofline=dict(bound='hbm', kernel='mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',

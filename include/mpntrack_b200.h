@@ -223,6 +223,14 @@ int mpn_mp_forward(const mpn_core_weights* h_w, const mpn_edge_layout* h_g,
 int mpn_attn_aggregate(const float* z, int64_t num_nodes, int64_t feat, const mpn_edge_layout* h_g,
                        const float* logits, float* flow_in, float* flow_out, void* stream);
 
+/* pl_module/pl_module.py:88-105  _compute_loss, tracking term: pos_weight = (#edges - #pos) / #pos (0 if no
+ * positive), loss = weight * sum over the classified steps of mean BCEWithLogits(logits[s], labels, pos_weight).
+ * logits [steps, E], labels [E] (0/1 floats).  Outputs: loss[1], pos_weight[1] (may be NULL) and, if grad is
+ * not NULL, grad[steps, E] = d loss / d logits.  Fixed-order reductions.  ws: mpn_weighted_bce_workspace() bytes. */
+int64_t mpn_weighted_bce_workspace(void);
+int mpn_weighted_bce(const float* logits, const float* labels, int64_t steps, int64_t num_edges, float weight,
+                     void* workspace, float* loss, float* pos_weight, float* grad, void* stream);
+
 /* Same contract as mpn_mp_forward (num_steps >= 1), evaluated on the tcgen05 tensor cores:
  * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).

@@ -374,3 +374,23 @@ def attn_aggregate(z, layout, logits):
     check(lib().mpn_attn_aggregate(ptr(z), n, feat, C.byref(g), ptr(lg), ptr(fin), ptr(fout), stream_ptr()),
           'attn_aggregate')
     return fin, fout
+
+
+def weighted_bce(logits, labels, weight=1.0, want_grad=False):
+    """Tracking loss over the classified steps: (loss scalar tensor, pos_weight tensor[, d loss / d logits]).
+    logits: [S, E] tensor or the list ``outputs['classified_edges']``.  pl_module/pl_module.py:88-105"""
+    if isinstance(logits, (list, tuple)):
+        logits = torch.stack([t.reshape(-1) for t in logits])
+    lg = _req(logits, torch.float32, 'logits')
+    lb = _req(labels.reshape(-1), torch.float32, 'edge_labels')
+    s, e = lg.shape
+    if lb.numel() != e:
+        raise ValueError(f'{lb.numel()} labels for {e} edges')
+    dev = lg.device
+    ws = _bytes(lib().mpn_weighted_bce_workspace(), dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    pw = torch.zeros(1, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(lg) if want_grad else None
+    check(lib().mpn_weighted_bce(ptr(lg), ptr(lb), s, e, float(weight), ptr(ws), ptr(loss), ptr(pw), ptr(grad),
+                                 stream_ptr()), 'weighted_bce')
+    return (loss, pw, grad) if want_grad else (loss, pw)

@@ -443,3 +443,19 @@ def test_node_encoder_tc_against_fp32():
         scale = float(ref.abs().max())
         assert float((got_32 - ref).abs().max()) <= 2e-5 * scale
         assert float((got_tc - ref).abs().max()) <= 2e-5 * scale, n
+
+
+def test_weighted_bce_loss_and_gradient_against_oracle():
+    """pl_module.py:88-105 on the GPU (loss value and d loss / d logits) against torch autograd on CPU."""
+    from mpntrackseg_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    for e, pos_frac in ((1000, 0.1), (37, 0.0), (5000, 0.5)):
+        logits = (torch.randn(3, e, generator=g) * 3).requires_grad_(True)
+        labels = (torch.rand(e, generator=g) < pos_frac).float()
+        ref = mpn_ref.weighted_bce_loss([logits[i].view(-1, 1) for i in range(3)], labels, tracking_weight=0.7)
+        ref.backward()
+        loss, pw, grad = ops.weighted_bce(logits.detach().to(dev()), labels.to(dev()), weight=0.7, want_grad=True)
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        pos = float(labels.sum())
+        assert abs(float(pw) - ((e - pos) / pos if pos else 0.0)) <= 1e-4 * max(1.0, e)
+        np.testing.assert_allclose(grad.cpu().numpy(), logits.grad.numpy(), rtol=2e-4, atol=1e-8)
