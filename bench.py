@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--graphs', type=int, default=8, help='frame windows per GPU per step')
+    ap.add_argument('--graphs', type=int, default=16, help='frame windows per GPU per step')
     ap.add_argument('--frames', type=int, default=15)
     ap.add_argument('--dets', type=int, default=150)
     ap.add_argument('--k', type=int, default=50)
@@ -123,7 +123,7 @@ class ClockSampler:
     """SM clock + throttle reasons sampled through NVML from a background thread DURING the timed
     region (an `nvidia-smi -lms` subprocess was found to slow the timed loop down through driver locks)."""
 
-    def __init__(self, gpu_index, period=0.05):
+    def __init__(self, gpu_index, period=0.005):
         import threading
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), 0, False
         self._stop = threading.Event()
@@ -324,7 +324,7 @@ def run_b200(a):
                      h2d_bytes_per_step=int(h2d_total), d2h_bytes_per_step=int(d2h_total),
                      graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3)),
             gpu_launches=int(launches),
-            roofline=dict(bound='hbm', kernel='mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
+            roofline=dict(bound='hbm', kernel='mp_edge_tc_kernel' if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
                           frac=achieved / peak if peak else None, traffic=None,
                           peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                           avg_launch_ms=avg_ms, launches=edge_launches,
