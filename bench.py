@@ -311,6 +311,13 @@ def run_b200(a):
         bytes_per_launch = edges * (200 + 4 * cls_frac) + nodes * 256
         avg_ms = float(prof_ms[0]) / edge_launches
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_mp_edge_tc_traffic.json')))
+            if os.environ.get('MPN_ENGINE', 'auto') != 'fp32':
+                traffic = tr['dram_bytes_per_edge_update'] * edges      # ncu dram read+write per edge-update x this launch's edges
+        except (OSError, KeyError, ValueError):
+            pass
         line = dict(
             metric=METRIC, value=NUM_STEPS_MP * all_edges * a.steps / (ms * 1e-3), unit=UNIT, n_gpus=world,
             steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak',
@@ -325,7 +332,7 @@ def run_b200(a):
                      graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3)),
             gpu_launches=int(launches),
             roofline=dict(bound='hbm', kernel='mp_edge_tc_kernel' if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
-                          frac=achieved / peak if peak else None, traffic=None,
+                          frac=achieved / peak if peak else None, traffic=traffic, algorithmic_bytes=bytes_per_launch,
                           peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                           avg_launch_ms=avg_ms, launches=edge_launches,
                           mp_phase_edge_updates_per_s=edges * edge_launches / (float(prof_ms[0] + prof_ms[1]) * 1e-3)
