@@ -109,14 +109,19 @@ int mpn_edge_feats_assemble(const int64_t* row, const int64_t* col, int64_t num_
  * Outputs: kept pairs (row<col) sorted by (row, col) with their ReID distance, and
  * graph_pair_ptr [G+1] (device + host): pair range of each window.  capacity = size of the out arrays
  * (sum over windows of N_g*min(k, N_g) is always enough); MPN_ENOSPC if exceeded.
- * workspace: mpn_knn_graph_workspace(N, sum_g N_g^2, G) bytes (dense fp32 distance blocks). */
+ * use_tensor_cores != 0 (and dim a multiple of 64, top_k >= 0): the dense distances come from a tcgen05 Gram
+ * contraction (fp16 hi/lo split) and only pre-rank; rows whose k-th / (k+1)-th neighbours lie within the error
+ * band are recomputed with the exact fp32 formula and re-ranked, and the distances returned for the kept pairs
+ * are always the exact ones -- the kept edge set equals the exact path's.  h_stats (host, may be NULL):
+ * [0] = 1 if the tensor-core path ran, [1] = number of rows that needed the exact repair.
+ * workspace: mpn_knn_graph_workspace(N, sum_g N_g^2, G) bytes (dense fp32 distance blocks + packed embeddings). */
 int64_t mpn_knn_graph_workspace(int64_t num_nodes, int64_t sum_sq_nodes, int64_t num_graphs);
 int mpn_knn_graph_pairs(const int64_t* frame_num, const int64_t* node_graph_ptr,
                         const int64_t* h_node_graph_ptr, int64_t num_graphs, const float* reid,
                         int64_t dim, int64_t top_k, int reciprocal, int64_t max_frame_dist,
-                        void* workspace, int64_t capacity, int64_t* out_row, int64_t* out_col,
-                        float* out_dist, int64_t* graph_pair_ptr, int64_t* h_graph_pair_ptr,
-                        void* stream);
+                        int use_tensor_cores, void* workspace, int64_t capacity, int64_t* out_row,
+                        int64_t* out_col, float* out_dist, int64_t* graph_pair_ptr,
+                        int64_t* h_graph_pair_ptr, int64_t* h_stats /*[2] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------ model: layout */
 

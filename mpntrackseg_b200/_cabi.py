@@ -48,8 +48,8 @@ SIGNATURES = {
     'mpn_edge_feats_assemble': (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32,
                                           c_vp, c_i64, c_vp, c_vp, c_vp]),
     'mpn_knn_graph_workspace': (c_i64, [c_i64, c_i64, c_i64]),
-    'mpn_knn_graph_pairs': (C.c_int, [c_vp, c_vp, c_i64p, c_i64, c_vp, c_i64, c_i64, C.c_int, c_i64, c_vp, c_i64,
-                                      c_vp, c_vp, c_vp, c_vp, c_i64p, c_vp]),
+    'mpn_knn_graph_pairs': (C.c_int, [c_vp, c_vp, c_i64p, c_i64, c_vp, c_i64, c_i64, C.c_int, c_i64, C.c_int, c_vp, c_i64,
+                                      c_vp, c_vp, c_vp, c_vp, c_i64p, c_i64p, c_vp]),
     'mpn_edge_layout_workspace': (c_i64, [c_i64, c_i64]),
     'mpn_edge_layout_build': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_vp]),
     'mpn_avgpool': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

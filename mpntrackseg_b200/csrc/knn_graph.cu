@@ -94,12 +94,14 @@ __global__ void __launch_bounds__(256) dist_blocks_kernel(const float* __restric
 __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restrict__ dense,
                                                             const int64_t* __restrict__ gptr, int64_t num_graphs,
                                                             const int64_t* __restrict__ doff, int64_t k,
+                                                            const int32_t* __restrict__ row_mask,
                                                             uint32_t* __restrict__ thr_key,
                                                             int32_t* __restrict__ thr_idx) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining;
   const int64_t i = blockIdx.x;
+  if (row_mask != nullptr && row_mask[i] == 0) return;
   int64_t lo = 0, hi = num_graphs;                                  // window of node i
   while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
   const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0;
@@ -215,6 +217,15 @@ __global__ void graph_pair_ptr_kernel(const int64_t* __restrict__ gptr, int64_t 
   }
 }
 
+int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim);
+int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
+                     int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s);
+int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
+                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
+                       const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
+                       cudaStream_t s);
+
 }  // namespace mpn
 
 using namespace mpn;
@@ -222,14 +233,17 @@ using namespace mpn;
 extern "C" {
 
 int64_t mpn_knn_graph_workspace(int64_t num_nodes, int64_t sum_sq_nodes, int64_t num_graphs) {
-  return align_up(sum_sq_nodes * 4, 256) + align_up((num_graphs + 1) * 8, 256) + 2 * align_up(num_nodes * 4, 256) +
-         align_up((num_nodes + 1) * 8, 256) + 1024;
+  const int64_t base = align_up(sum_sq_nodes * 4, 256) + align_up((num_graphs + 1) * 8, 256) +
+                       2 * align_up(num_nodes * 4, 256) + align_up((num_nodes + 1) * 8, 256) + 2048;
+  // tensor-core path: packed fp16 hi/lo image of the embeddings (dim <= 512 covered) + per-node scalars
+  return base + gram_workspace_bytes(num_nodes, num_nodes / 128 + num_graphs, num_graphs, 512) + 256;
 }
 
 int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr, int64_t num_graphs,
                         const float* reid, int64_t dim, int64_t top_k, int reciprocal, int64_t max_frame_dist,
-                        void* ws, int64_t capacity, int64_t* out_row, int64_t* out_col, float* out_dist,
-                        int64_t* graph_pair_ptr, int64_t* h_graph_pair_ptr, void* stream) {
+                        int use_tensor_cores, void* ws, int64_t capacity, int64_t* out_row, int64_t* out_col,
+                        float* out_dist, int64_t* graph_pair_ptr, int64_t* h_graph_pair_ptr, int64_t* h_stats,
+                        void* stream) {
   MPN_CHECK_ARG(num_graphs >= 1 && h_gptr && gptr && frame && reid && ws, "knn_graph_pairs: null / empty arguments");
   MPN_CHECK_ARG(out_row && out_col && out_dist && graph_pair_ptr && h_graph_pair_ptr, "knn_graph_pairs: null outputs");
   MPN_CHECK_ARG(num_graphs <= 65535, "knn_graph_pairs: at most 65535 windows per call");
@@ -250,24 +264,52 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   int32_t* ti = cv.take<int32_t>(n);
   int64_t* row_start = cv.take<int64_t>(n + 1);
   const int prune = top_k >= 0 ? 1 : 0;
+  // Gram distances only pre-rank (they are repaired / recomputed exactly below); without pruning every
+  // distance is an output, so the exact kernel is used directly.
+  const bool tc = use_tensor_cores && prune && dim % 64 == 0 && dim <= 512 && reinterpret_cast<uintptr_t>(reid) % 16 == 0;
+  int32_t* status = reinterpret_cast<int32_t*>(cv.take<int32_t>(4));
+  float* norm2 = nullptr;
+  int32_t* amb = nullptr;
+  int32_t* amb_count = nullptr;
+  int rc = MPN_OK;
+  MPN_CUDA(cudaMemsetAsync(status, 0, 16, s));
 
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff); count_launch();
-  const int64_t nt = ceil_div(max_n, DT);
-  dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)num_graphs);
-  dist_blocks_kernel<<<grid, 256, 0, s>>>(reid, dim, frame, gptr, doff, max_frame_dist, dense); count_launch();
+  if (tc) {
+    rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
+                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, s);
+    if (rc) return rc;
+  } else {
+    const int64_t nt = ceil_div(max_n, DT);
+    dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)num_graphs);
+    dist_blocks_kernel<<<grid, 256, 0, s>>>(reid, dim, frame, gptr, doff, max_frame_dist, dense); count_launch();
+  }
   if (prune) {
-    batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, tk, ti); count_launch();
+    batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti); count_launch();
+    if (tc) {                                                       // repair rows whose top-k set is not certain
+      rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
+                              amb, amb_count, s);
+      if (rc) return rc;
+      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti); count_launch();
+    }
   }
   const unsigned wgrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16);
   knn_pairs_kernel<false><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
                                                reciprocal, row_start, nullptr, nullptr, nullptr); count_launch();
   MPN_LAUNCH_CHECK();
-  int rc = exclusive_scan_i64(row_start, row_start, n, s);
+  rc = exclusive_scan_i64(row_start, row_start, n, s);
   if (rc) return rc;
   graph_pair_ptr_kernel<<<(unsigned)ceil_div(num_graphs + 1, 256), 256, 0, s>>>(gptr, num_graphs, n, row_start, graph_pair_ptr);
   count_launch();
   MPN_CUDA(cudaMemcpyAsync(h_graph_pair_ptr, graph_pair_ptr, 8 * (num_graphs + 1), cudaMemcpyDeviceToHost, s));
+  int32_t h_flags[2] = {0, 0};                                      // fp16 overflow in the Gram kernel, #ambiguous rows
+  MPN_CUDA(cudaMemcpyAsync(&h_flags[0], status, 4, cudaMemcpyDeviceToHost, s));
+  if (tc) MPN_CUDA(cudaMemcpyAsync(&h_flags[1], amb_count, 4, cudaMemcpyDeviceToHost, s));
   MPN_CUDA(cudaStreamSynchronize(s));
+  if (tc && h_flags[0] != 0)                                        // embeddings beyond the fp16 range: exact kernel
+    return mpn_knn_graph_pairs(frame, gptr, h_gptr, num_graphs, reid, dim, top_k, reciprocal, max_frame_dist, 0, ws,
+                               capacity, out_row, out_col, out_dist, graph_pair_ptr, h_graph_pair_ptr, h_stats, stream);
+  if (h_stats != nullptr) { h_stats[0] = tc ? 1 : 0; h_stats[1] = h_flags[1]; }
   const int64_t total = h_graph_pair_ptr[num_graphs];
   if (total > capacity) {
     set_error("knn_graph_pairs: %lld pairs exceed the output capacity %lld", (long long)total, (long long)capacity);
@@ -276,6 +318,8 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   knn_pairs_kernel<true><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
                                               reciprocal, row_start, out_row, out_col, out_dist); count_launch();
   MPN_LAUNCH_CHECK();
+  if (tc && total > 0)                                              // the edge feature is always the exact distance
+    return mpn_pair_reid_dist(reid, n, dim, out_row, out_col, total, out_dist, stream);
   return MPN_OK;
 }
 

@@ -170,7 +170,8 @@ class GraphBatch(object):
         return Graph(x=x, x_ext=None, edge_attr=ea, edge_index=ei)
 
 
-def build_window_graphs(windows, dataset_params, fps, inference_mode=False, max_frame_dist=None, device=None):
+def build_window_graphs(windows, dataset_params, fps, inference_mode=False, max_frame_dist=None, device=None,
+                        engine=None):
     """Edge construction + assembly (``MOTGraph._get_edge_ixs`` + ``construct_graph_object``,
     reference: data/mot_graph.py:195-221, 283-316) for a list of windows at once, on the GPU, with one
     host synchronisation.  Each window is a mapping with ``frame, bb_height, bb_width, feet_x, feet_y``
@@ -185,7 +186,7 @@ def build_window_graphs(windows, dataset_params, fps, inference_mode=False, max_
     mfd = dataset_params['max_frame_dist'] if max_frame_dist is None else max_frame_dist
     k = None if inference_mode else dataset_params['top_k_nns']
     pairs, dist, pair_ptr = ops.knn_graph_pairs(frame, node_ptr, reid, k, dataset_params['reciprocal_k_nns'],
-                                                -1 if mfd == 'max' else int(mfd))
+                                                -1 if mfd == 'max' else int(mfd), engine=engine)
     use = dataset_params['edge_feats_to_use']
     with_dist = 'emb_dist' in use
     attr, edge_index = ops.edge_feats_assemble(pairs, frame.float(), cat('bb_height', torch.float32),

@@ -108,7 +108,10 @@ def edge_feats_assemble(pairs, frame_f32, bb_height, bb_width, feet_x, feet_y, f
     return attr, eidx
 
 
-def knn_graph_pairs(frame_num, node_graph_ptr_host, reid, top_k, reciprocal, max_frame_dist=-1):
+LAST_KNN_STATS = [0, 0]      # [tensor-core path used, rows repaired exactly] of the last knn_graph_pairs call
+
+
+def knn_graph_pairs(frame_num, node_graph_ptr_host, reid, top_k, reciprocal, max_frame_dist=-1, engine=None):
     """Batched edge construction: (pairs [2,P] int64 batch-global ids sorted by (row,col), dist [P],
     graph_pair_ptr list[G+1]).  node_graph_ptr_host: python list / CPU tensor of G+1 node offsets.
     data/mot_graph.py:195-221 for every window of the batch in one pass."""
@@ -131,9 +134,12 @@ def knn_graph_pairs(frame_num, node_graph_ptr_host, reid, top_k, reciprocal, max
     dist = torch.empty(cap, dtype=torch.float32, device=dev)
     gpp = torch.empty(g + 1, dtype=torch.int64, device=dev)
     h_gpp = (C.c_int64 * (g + 1))()
+    h_stats = (C.c_int64 * 2)()
+    use_tc = int((engine or default_engine()) != 'fp32')
     check(lib().mpn_knn_graph_pairs(ptr(f), ptr(d_ptr), h_ptr, g, ptr(reid), reid.shape[1], k, int(bool(reciprocal)),
-                                    int(max_frame_dist), ptr(ws), cap, ptr(pairs[0]), ptr(pairs[1]), ptr(dist), ptr(gpp),
-                                    h_gpp, stream_ptr()), 'knn_graph_pairs')
+                                    int(max_frame_dist), use_tc, ptr(ws), cap, ptr(pairs[0]), ptr(pairs[1]), ptr(dist),
+                                    ptr(gpp), h_gpp, h_stats, stream_ptr()), 'knn_graph_pairs')
+    LAST_KNN_STATS[:] = list(h_stats)
     hg = list(h_gpp)
     p = hg[-1]
     return torch.stack((pairs[0, :p], pairs[1, :p])) if p != cap else pairs, dist[:p], hg

@@ -459,3 +459,41 @@ def test_weighted_bce_loss_and_gradient_against_oracle():
         pos = float(labels.sum())
         assert abs(float(pw) - ((e - pos) / pos if pos else 0.0)) <= 1e-4 * max(1.0, e)
         np.testing.assert_allclose(grad.cpu().numpy(), logits.grad.numpy(), rtol=2e-4, atol=1e-8)
+
+
+def test_tensor_core_gram_knn_equals_exact_path_and_repairs_near_ties():
+    """KNN edge set from the tcgen05 Gram distances == exact fp32 path == oracle, including windows whose
+    embeddings produce exact ties / sub-band gaps at the k boundary (those rows must take the exact repair)."""
+    from mpntrackseg_b200 import ops
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    ds = default_dataset_params(top_k_nns=9, frames_per_graph=8)
+    wins = [synth.make_window(T=8, D=20, k=9, seed=50 + i) for i in range(3)]
+    # window 1: duplicated embeddings (exact distance ties); window 2: tiny perturbations (gaps below the band)
+    g = torch.Generator().manual_seed(3)
+    wins[1].reid = wins[1].reid[torch.arange(wins[1].N) % 40].contiguous()
+    base = wins[2].reid[torch.arange(wins[2].N) % 40]
+    wins[2].reid = (base + 1e-7 * torch.randn(base.shape, generator=g)).contiguous()
+    inputs = [dict(synth.det_columns(w), reid=w.reid, x=w.x) for w in wins]
+    tc = build_window_graphs(inputs, ds, fps=30.0, engine='tc')
+    stats = list(ops.LAST_KNN_STATS)
+    ex = build_window_graphs(inputs, ds, fps=30.0, engine='fp32')
+    assert stats[0] == 1 and stats[1] > 0, stats            # tensor-core path ran and repaired some rows
+    assert ops.LAST_KNN_STATS[0] == 0
+    assert tc.pair_ptr == ex.pair_ptr
+    assert torch.equal(tc.edge_index, ex.edge_index)
+    np.testing.assert_allclose(tc.edge_attr.cpu().numpy(), ex.edge_attr.cpu().numpy(), rtol=3e-6, atol=1e-6)
+    ref = graph_ref.build_graph(wins[0].frame, wins[0].reid, synth.det_columns(wins[0]), 30.0, ds)
+    assert torch.equal(tc.graph(0).edge_index.cpu(), ref['edge_index'])
+
+
+def test_tensor_core_gram_config2_window_no_repairs_needed():
+    from mpntrackseg_b200 import ops
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    w = synth.make_window(T=15, D=150, k=50, seed=4)
+    ds = default_dataset_params(top_k_nns=50, frames_per_graph=15)
+    inp = [dict(synth.det_columns(w), reid=w.reid, x=w.x)]
+    tc = build_window_graphs(inp, ds, fps=30.0, engine='tc')
+    repaired = ops.LAST_KNN_STATS[1]
+    ex = build_window_graphs(inp, ds, fps=30.0, engine='fp32')
+    assert torch.equal(tc.edge_index, ex.edge_index)
+    assert repaired <= w.N // 20, repaired                  # well-separated data: (almost) nothing to repair
