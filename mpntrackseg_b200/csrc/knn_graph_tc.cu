@@ -206,54 +206,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_blocks_kernel(GramArgs a) {
   if (warp == 0) tmem_dealloc<512>(*tmem_slot);
 }
 
-__device__ __forceinline__ uint32_t okey(float f) {
-  uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// One CTA per row: is the top-k SET of this row certain given the error band of the Gram distances?
-// ambiguous <=> an entry outside the top-k lies within the band above the k-th value (in d^2).
-__global__ void __launch_bounds__(256) row_ambiguity_kernel(const float* __restrict__ dense, const int64_t* __restrict__ gptr,
-                                                            int64_t num_graphs, const int64_t* __restrict__ doff,
-                                                            const float* __restrict__ norm2, const uint32_t* __restrict__ thr_key,
-                                                            const int32_t* __restrict__ thr_idx, float beta,
-                                                            int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
-  __shared__ float s_min[8];
-  __shared__ float s_nmax[8];
-  const int64_t i = blockIdx.x;
-  int64_t lo = 0, hi = num_graphs;
-  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
-  const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0;
-  const float* rowp = dense + doff[lo] + (i - n0) * n;
-  const uint32_t tk = thr_key[i];
-  const int32_t ti = thr_idx[i];
-  if (tk == 0xffffffffu) { if (threadIdx.x == 0) amb[i] = 0; return; }      // k >= row length: everything is in
-  float mn = INFINITY, nmax = 0.f;
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-    const float v = rowp[j];
-    const uint32_t key = okey(v);
-    const bool outside = key > tk || (key == tk && j > ti);
-    if (outside) mn = fminf(mn, v);
-    nmax = fmaxf(nmax, norm2[n0 + j]);
-  }
-  for (int d = 16; d > 0; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, d)); }
-  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = mn; s_nmax[threadIdx.x >> 5] = nmax; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) { mn = fminf(mn, s_min[q]); nmax = fmaxf(nmax, s_nmax[q]); }
-    // k-th value from its key
-    const uint32_t u = (tk & 0x80000000u) ? (tk & 0x7fffffffu) : ~tk;
-    const float vk = __uint_as_float(u);
-    int flag = 0;
-    if (isfinite(vk) && isfinite(mn)) {
-      const float band = beta * (norm2[i] + nmax);                           // absolute error bound on d^2
-      flag = (mn * mn - vk * vk) <= 2.f * band ? 1 : 0;
-    }
-    amb[i] = flag;
-    if (flag) atomicAdd(amb_count, 1);
-  }
-}
-
 // Exact fp32 row (reference formula, sequential over the feature dimension) for the flagged rows.
 __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict__ reid, int64_t dim,
                                                          const int64_t* __restrict__ frame, const int64_t* __restrict__ gptr,
@@ -342,12 +294,9 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
 }
 
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
-                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
-                       const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
+                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const int32_t* amb,
                        cudaStream_t s) {
   using namespace gram;
-  row_ambiguity_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(dense, gptr, num_graphs, doff, norm2, thr_key, thr_idx, beta,
-                                                         amb, amb_count); count_launch();
   exact_rows_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(reid, dim, frame, gptr, num_graphs, doff, max_dist, amb, dense);
   count_launch();
   MPN_LAUNCH_CHECK();

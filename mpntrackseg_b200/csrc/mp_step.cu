@@ -215,9 +215,9 @@ __global__ void __launch_bounds__(256) mp_node_kernel(const int32_t* __restrict_
   constexpr int DN = W::DN;
   __shared__ float s_w[2 * DN * DN];   // Wt[in][out]
   __shared__ float s_b[DN];
-  for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
-    const int i = idx / DN, o = idx - i * DN;
-    s_w[idx] = node_w[o * 2 * DN + i];
+  for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {     // coalesced along a weight row
+    const int o = idx / (2 * DN), i = idx - o * 2 * DN;
+    s_w[i * DN + o] = node_w[idx];
   }
   for (int o = threadIdx.x; o < DN; o += blockDim.x) s_b[o] = node_b[o];
   __syncthreads();

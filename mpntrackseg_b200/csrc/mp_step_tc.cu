@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
                                                          int32_t* __restrict__ status) {
   __shared__ float s_w[64 * EH];     // [i][o], i over W0 columns 0..63
   __shared__ float s_b[EH];
-  for (int idx = threadIdx.x; idx < 64 * EH; idx += blockDim.x) {
-    const int i = idx / EH, o = idx % EH;
-    s_w[idx] = w0[o * 160 + i];
+  for (int idx = threadIdx.x; idx < 64 * EH; idx += blockDim.x) {        // coalesced along a weight row
+    const int o = idx / 64, i = idx - o * 64;
+    s_w[i * EH + o] = w0[o * 160 + i];
   }
   for (int o = threadIdx.x; o < EH; o += blockDim.x) s_b[o] = b0[o];
   __syncthreads();
@@ -189,14 +189,15 @@ __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict_
   __shared__ float s_wn[2 * DN * DN];   // [in][out]
   __shared__ float s_bn[DN];
   __shared__ float s_w0[DN * EH];       // [i][o] over W0 columns 32..63
+  // coalesced global reads (consecutive threads walk a weight row), transposed on the way into smem
   for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
-    const int i = idx / DN, o = idx - i * DN;
-    s_wn[idx] = node_w[o * 2 * DN + i];
+    const int o = idx / (2 * DN), i = idx - o * 2 * DN;
+    s_wn[i * DN + o] = node_w[idx];
   }
   for (int o = threadIdx.x; o < DN; o += blockDim.x) s_bn[o] = node_b[o];
-  for (int idx = threadIdx.x; idx < DN * EH; idx += blockDim.x) {
-    const int i = idx / EH, o = idx % EH;
-    s_w0[idx] = w0[o * 160 + 32 + i];
+  for (int idx = threadIdx.x; idx < EH * DN; idx += blockDim.x) {
+    const int o = idx / DN, i = idx - o * DN;
+    s_w0[i * EH + o] = w0[o * 160 + 32 + i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -781,7 +782,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   }
   const int sms = sm_count();
   tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in); count_launch();
-  const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 8);
+  const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 4);
   tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, status);
   count_launch();
   if (e > 0) {
