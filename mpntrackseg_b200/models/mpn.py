@@ -265,6 +265,12 @@ class MOTMPNet(nn.Module):
         encoder instead of a host sync + fallback here."""
         return self.encode_nodes_list([x], status=status)
 
+    def encode_pooled(self, pooled, engine=None, status=None):
+        """Node MLP on already pooled features [N, C] (one launch for any number of windows)."""
+        lins = self.encoder.node_model.linears()
+        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins],
+                                engine=engine or self.engine, status=status)
+
     def encode_nodes_list(self, xs, engine=None, status=None):
         """Node encoder over several windows' features in ONE kernel launch: every window is pooled into
         its slice of a [N_total, C] buffer, then the whole buffer goes through the MLP."""
