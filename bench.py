@@ -123,7 +123,7 @@ class ClockSampler:
     """SM clock + throttle reasons sampled through NVML from a background thread DURING the timed
     region (an `nvidia-smi -lms` subprocess was found to slow the timed loop down through driver locks)."""
 
-    def __init__(self, gpu_index, period=0.005):
+    def __init__(self, gpu_index, period=0.02):
         import threading
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), 0, False
         self._stop = threading.Event()
@@ -191,25 +191,33 @@ def run_b200(a):
 
     wins = make_windows(a, rank, world)
     gen = torch.Generator(device=dev).manual_seed(rank)
-    host, devin = [], []
+    fps = wins[0].fps
+    node_ptr = [0]
+    for w in wins:
+        node_ptr.append(node_ptr[-1] + w.N)
+    # the job's detection table: one set of columns for all windows (the way the reference holds a
+    # sequence's graph_df) + one node-feature tensor per window
+    cols = {k: torch.cat([torch.from_numpy(synth.det_columns(w)[k]) for w in wins])
+            for k in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+    cols['reid'] = torch.cat([w.reid for w in wins])
+    host = {k: v.pin_memory() for k, v in cols.items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    host['x'], devin['x'] = [], []
     for w in wins:
         shape = (w.N, 2048) if a.pooled else (w.N, 2048, 8, 4)
         x = torch.randn(shape, generator=gen, device=dev).abs_()
-        cols = {k: torch.from_numpy(v) for k, v in synth.det_columns(w).items()}
-        h = dict(x=x.cpu().pin_memory(), reid=w.reid.pin_memory(), **{k: v.pin_memory() for k, v in cols.items()})
-        host.append(h)
-        devin.append({k: v.to(dev) for k, v in h.items()})
-        devin[-1]['x'] = x
-    fps = wins[0].fps
-    h2d_bytes = sum(t.numel() * t.element_size() for h in host for t in h.values())
+        devin['x'].append(x)
+        host['x'].append(x.cpu().pin_memory())
+    h2d_bytes = sum(t.numel() * t.element_size() for k, t in host.items() if k != 'x') + \
+        sum(t.numel() * t.element_size() for t in host['x'])
 
     from mpntrackseg_b200 import ops
-    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    from mpntrackseg_b200.data.mot_graph import build_graph_batch
 
     def step(inputs):
         """One pass of the hot path over the GPU's windows: batched KNN graph build + edge features,
         node / edge encoders, 12 MP steps + classifier (block-diagonal batch)."""
-        batch = build_window_graphs(inputs, ds, fps, device=dev)
+        batch = build_graph_batch(inputs, node_ptr, ds, fps, device=dev)
         with torch.no_grad():
             out = model.forward_batch(batch)
         return batch, out
@@ -221,27 +229,29 @@ def run_b200(a):
         copied first, the big node-feature tensors follow on a copy stream and each window's encoder
         waits only for its own x (H2D overlaps the graph build); logits are read back."""
         main = torch.cuda.current_stream()
-        inputs, events = [], []
+        events = []
         with torch.cuda.stream(copy_stream):
-            for h in host:
-                inputs.append({k: v.to(dev, non_blocking=True) for k, v in h.items() if k != 'x'})
+            inputs = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != 'x'}
             small = torch.cuda.Event()
             small.record(copy_stream)
-            for h, d in zip(host, inputs):
-                d['x'] = h['x'].to(dev, non_blocking=True)
+            inputs['x'] = []
+            for hx in host['x']:
+                inputs['x'].append(hx.to(dev, non_blocking=True))
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append(ev)
         main.wait_event(small)
-        batch = build_window_graphs(inputs, ds, fps, device=dev)
+        for v in inputs.values():
+            if torch.is_tensor(v):
+                v.record_stream(main)
+        batch = build_graph_batch(inputs, node_ptr, ds, fps, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         pooled = torch.empty((batch.num_nodes, 2048), dtype=torch.float32, device=dev)
         with torch.no_grad():
-            for i, (d, ev) in enumerate(zip(inputs, events)):
+            for i, (x, ev) in enumerate(zip(inputs['x'], events)):
                 main.wait_event(ev)                                   # this window's node features have landed
-                d['x'].record_stream(main)
-                ops.avgpool(d['x'] if d['x'].dim() > 2 else d['x'][:, :, None, None],
-                            out=pooled[batch.node_ptr[i]:batch.node_ptr[i + 1]])
+                x.record_stream(main)
+                ops.avgpool(x if x.dim() > 2 else x[:, :, None, None], out=pooled[node_ptr[i]:node_ptr[i + 1]])
             batch.xs = model.encode_pooled(pooled, status=flags)      # one encoder launch for all windows
             out = model.forward_batch(batch, encoded=True)
         res = out.logits[-1].cpu()                                    # D2H of the result (last step's logits)

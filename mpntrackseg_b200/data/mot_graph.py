@@ -180,22 +180,35 @@ def build_window_graphs(windows, dataset_params, fps, inference_mode=False, max_
     node_ptr = [0]
     for w in windows:
         node_ptr.append(node_ptr[-1] + int(w['reid'].shape[0]))
-    cat = lambda name, dt: torch.cat([_col(w, name, dev).to(dt).view(-1) for w in windows])
-    frame = cat('frame', torch.int64)
-    reid = torch.cat([w['reid'].to(dev, torch.float32) for w in windows])
+    table = {name: torch.cat([_col(w, name, dev).view(-1) for w in windows])
+             for name in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+    table['reid'] = torch.cat([w['reid'].to(dev, torch.float32) for w in windows])
+    table['x'] = [w['x'] if w['x'].is_cuda else w['x'].to(dev) for w in windows]
+    return build_graph_batch(table, node_ptr, dataset_params, fps, inference_mode, max_frame_dist, dev, engine)
+
+
+def build_graph_batch(table, node_ptr, dataset_params, fps, inference_mode=False, max_frame_dist=None, device=None,
+                      engine=None):
+    """Same as ``build_window_graphs`` for a detection table that is already ONE set of columns (the way
+    the reference holds a sequence's ``graph_df``): ``table`` maps ``frame, bb_height, bb_width, feet_x,
+    feet_y`` to [N_total] tensors, ``reid`` to [N_total,256] and ``x`` to the node features (one tensor
+    or a list with one tensor per window); window g owns rows ``node_ptr[g]:node_ptr[g+1]``."""
+    dev = device or torch.device('cuda')
+    col = lambda name, dt: table[name].to(dev, dt).view(-1)
+    frame = col('frame', torch.int64)
+    reid = table['reid'].to(dev, torch.float32)
     mfd = dataset_params['max_frame_dist'] if max_frame_dist is None else max_frame_dist
     k = None if inference_mode else dataset_params['top_k_nns']
     pairs, dist, pair_ptr = ops.knn_graph_pairs(frame, node_ptr, reid, k, dataset_params['reciprocal_k_nns'],
                                                 -1 if mfd == 'max' else int(mfd), engine=engine)
     use = dataset_params['edge_feats_to_use']
     with_dist = 'emb_dist' in use
-    attr, edge_index = ops.edge_feats_assemble(pairs, frame.float(), cat('bb_height', torch.float32),
-                                               cat('bb_width', torch.float32), cat('feet_x', torch.float32),
-                                               cat('feet_y', torch.float32), fps, dist if with_dist else None)
+    attr, edge_index = ops.edge_feats_assemble(pairs, frame.float(), col('bb_height', torch.float32),
+                                               col('bb_width', torch.float32), col('feet_x', torch.float32),
+                                               col('feet_y', torch.float32), fps, dist if with_dist else None)
     order = ('secs_time_dists', 'norm_feet_x_dists', 'norm_feet_y_dists', 'bb_height_dists', 'bb_width_dists')
     wanted = [order.index(n) for n in use if n in order] + ([5] if with_dist else [])
     if wanted != list(range(attr.shape[1])):
         attr = attr[:, wanted].contiguous()
-    xs = [w['x'] if w['x'].is_cuda else w['x'].to(dev) for w in windows]
-    return GraphBatch(xs, node_ptr, edge_index, attr, pair_ptr,
+    return GraphBatch(table['x'], node_ptr, edge_index, attr, pair_ptr,
                       torch.cat((dist, dist)) if inference_mode else None)
