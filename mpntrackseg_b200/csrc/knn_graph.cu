@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
                                                             const int32_t* __restrict__ row_mask,
                                                             uint32_t* __restrict__ thr_key,
                                                             int32_t* __restrict__ thr_idx,
-                                                            const float* __restrict__ norm2, float beta,
+                                                            const float* __restrict__ norm2,
+                                                            const float* __restrict__ win_nmax, float beta,
                                                             int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
@@ -178,11 +179,10 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
   __syncthreads();
   // ---- is the top-k set certain under the Gram error band?
   const int32_t tfound = s_found;
-  float mn = INFINITY, nmax = 0.f;
+  float mn = INFINITY, nmax = win_nmax[lo];                          // max ||a_j||^2 over the window
   auto visit = [&](uint32_t key, int64_t j) {
     const bool outside = key > tau || (key == tau && j > tfound);
     if (outside) { const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key; mn = fminf(mn, __uint_as_float(u)); }
-    nmax = fmaxf(nmax, norm2[n0 + j]);
   };
   if (in_regs) {
 #pragma unroll
@@ -190,11 +190,11 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
   } else {
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) visit(order_key_f(rowp[j]), j);
   }
-  for (int d = 16; d > 0; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, d)); nmax = fmaxf(nmax, __shfl_xor_sync(kFullMask, nmax, d)); }
-  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = mn; s_red[8 + (threadIdx.x >> 5)] = nmax; }
+  for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, d));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) { mn = fminf(mn, s_red[q]); nmax = fmaxf(nmax, s_red[8 + q]); }
+    for (int q = 1; q < 8; ++q) mn = fminf(mn, s_red[q]);
     const uint32_t u = (tau & 0x80000000u) ? (tau & 0x7fffffffu) : ~tau;
     const float vk = __uint_as_float(u);
     int flag = 0;
@@ -271,7 +271,8 @@ __global__ void graph_pair_ptr_kernel(const int64_t* __restrict__ gptr, int64_t 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim);
 int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
                      int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
-                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s);
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out,
+                     const float** win_nmax_out, cudaStream_t s);
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
                        int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const int32_t* amb,
                        cudaStream_t s);
@@ -321,13 +322,14 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   float* norm2 = nullptr;
   int32_t* amb = nullptr;
   int32_t* amb_count = nullptr;
+  const float* win_nmax = nullptr;
   int rc = MPN_OK;
   MPN_CUDA(cudaMemsetAsync(status, 0, 16, s));
 
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff); count_launch();
   if (tc) {
     rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
-                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, s);
+                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, &win_nmax, s);
     if (rc) return rc;
   } else {
     const int64_t nt = ceil_div(max_n, DT);
@@ -336,12 +338,12 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   }
   if (prune) {
     batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti,
-                                                      tc ? norm2 : nullptr, 2e-6f, amb, amb_count); count_launch();
+                                                      tc ? norm2 : nullptr, win_nmax, 2e-6f, amb, amb_count); count_launch();
     if (tc) {                                                       // repair rows whose top-k set is not certain
       rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, amb, s);
       if (rc) return rc;
-      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti, nullptr, 0.f,
-                                                        nullptr, nullptr); count_launch();
+      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti, nullptr, nullptr,
+                                                        0.f, nullptr, nullptr); count_launch();
     }
   }
   const unsigned wgrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16);

@@ -32,7 +32,8 @@ __device__ __forceinline__ int slab_off(int n, int k16) {
 // warp per node: packed fp16 hi/lo image of its row inside its 128-row tile, ||a||^2 and sum(a).
 __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, const int64_t* __restrict__ gptr,
                                  int64_t num_graphs, const int64_t* __restrict__ tile_off, int64_t num_nodes,
-                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1) {
+                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1,
+                                 int* __restrict__ win_nmax_bits) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -54,7 +55,7 @@ __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, co
       *reinterpret_cast<__half*>(base + (KC / 16) * SLAB) = l;
     }
     for (int d = 16; d > 0; d >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); }
-    if (lane == 0) { norm2[i] = s2; sum1[i] = s1; }
+    if (lane == 0) { norm2[i] = s2; sum1[i] = s1; atomicMax(&win_nmax_bits[lo], __float_as_int(s2)); }   // s2 >= 0
   }
 }
 
@@ -247,14 +248,15 @@ __global__ void tile_offsets_kernel(const int64_t* __restrict__ gptr, int64_t nu
 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim) {
   return align_up(total_tiles * (dim / gram::KC) * gram::CHUNK_BYTES, 256) + 2 * align_up(num_nodes * 4, 256) +
-         align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + 1024;
+         align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + align_up(num_graphs * 4, 256) + 1024;
 }
 
 // Fills the dense blocks with Gram distances, ranks, then repairs ambiguous rows exactly.
 // `rank_rows(mask)` is provided by knn_graph.cu (batch_row_kth_kernel launcher).
 int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
                      int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
-                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s) {
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, const float** win_nmax_out,
+                     cudaStream_t s) {
   using namespace gram;
   const int64_t n = h_gptr[num_graphs];
   int64_t total_tiles = 0, max_tiles = 0;
@@ -269,11 +271,13 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
   float* sum1 = cv.take<float>(n);
   int64_t* tile_off = cv.take<int64_t>(num_graphs + 1);
   int32_t* amb = cv.take<int32_t>(n + 1);
+  int* nmax_bits = cv.take<int>(num_graphs);
+  MPN_CUDA(cudaMemsetAsync(nmax_bits, 0, 4 * num_graphs, s));
   MPN_CUDA(cudaMemsetAsync(img, 0, total_tiles * (dim / KC) * CHUNK_BYTES, s));
   MPN_CUDA(cudaMemsetAsync(amb + n, 0, 4, s));
   tile_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, tile_off); count_launch();
   pack_reid_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16), 256, 0, s>>>(
-      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1); count_launch();
+      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1, nmax_bits); count_launch();
   static bool attr_set = false;
   if (!attr_set) {
     MPN_CUDA(cudaFuncSetAttribute(gram_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -290,6 +294,7 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
   gram_blocks_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a); count_launch();
   MPN_LAUNCH_CHECK();
   *norm2_out = norm2; *amb_out = amb; *amb_count_out = amb + n;
+  *win_nmax_out = reinterpret_cast<const float*>(nmax_bits);
   return MPN_OK;
 }
 
