@@ -35,8 +35,8 @@ NUM_CLASS_STEPS = 11
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--graphs', type=int, default=16, help='frame windows per GPU per step')
     ap.add_argument('--frames', type=int, default=15)
@@ -270,7 +270,11 @@ def run_b200(a):
     edges = batch.num_edges
     nodes = batch.num_nodes
 
-    # ---- timed region: device-resident inputs
+    # ---- timed region: device-resident inputs (Python's cyclic GC is paused: a gen-2 collection inside
+    #      a 7 ms step shows up as a 20-40 ms outlier)
+    import gc
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get('MPN_BENCH_NO_SAMPLER') else None
     lib.mpn_profile_begin()
     launches0 = lib.mpn_launch_count()
@@ -303,6 +307,7 @@ def run_b200(a):
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1)
+    gc.enable()
 
     from mpntrackseg_b200.sharding import reduce_step_stats
     ms, (all_edges, all_nodes, h2d_total, d2h_total) = reduce_step_stats(ms, [edges, nodes, h2d_bytes, d2h], device=dev)

@@ -142,6 +142,20 @@ static int exclusive_scan_impl(const T* in, T* out, int64_t n, cudaStream_t stre
     return MPN_OK;
   }
   const int64_t chunks = ceil_div(n, kScanChunk);
+  {
+    // keep the stream-ordered pool's memory across synchronisations (default threshold 0 would hand it
+    // back to the OS at every sync and re-allocate on the next call)
+    static bool pool_ready = false;
+    if (!pool_ready) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready = true;
+    }
+  }
   T* totals = nullptr;
   MPN_CUDA(cudaMallocAsync(&totals, sizeof(T) * (chunks + 1), stream));
   scan_chunk_totals<T><<<(unsigned)chunks, kScanThreads, 0, stream>>>(in, totals, n); count_launch();
