@@ -127,30 +127,72 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
     const int64_t j = threadIdx.x + 256 * q;
     keys[q] = (in_regs && j < n) ? order_key_f(rowp[j]) : 0xffffffffu;
   }
-  if (threadIdx.x == 0) { s_prefix = 0u; s_remaining = (int)k; }
+  // Radix select over 8-bit digits.  Distances of one row share their leading bits (same exponent), so the
+  // digits above the highest bit in which the finite keys differ are skipped: fewer passes and, more
+  // importantly, a first histogram that is spread over its bins instead of one contended counter.
+  __shared__ uint32_t s_kmin[8], s_kmax[8];
+  __shared__ int s_nfin[8];
+  int hi_bit = 31;
   uint32_t mask = 0u;
-  for (int shift = 24; shift >= 0; shift -= 8) {
+  if (in_regs) {
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    int nfin = 0;
+#pragma unroll
+    for (int q = 0; q < KTH_MAXV; ++q)
+      if (threadIdx.x + 256 * q < n && keys[q] < 0xff800000u) {      // finite, non-negative distance
+        kmin = keys[q] < kmin ? keys[q] : kmin;
+        kmax = keys[q] > kmax ? keys[q] : kmax;
+        ++nfin;
+      }
+    for (int d = 16; d > 0; d >>= 1) {
+      const uint32_t a = __shfl_xor_sync(kFullMask, kmin, d), b = __shfl_xor_sync(kFullMask, kmax, d);
+      kmin = a < kmin ? a : kmin;
+      kmax = b > kmax ? b : kmax;
+      nfin += __shfl_xor_sync(kFullMask, nfin, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_kmin[threadIdx.x >> 5] = kmin; s_kmax[threadIdx.x >> 5] = kmax; s_nfin[threadIdx.x >> 5] = nfin; }
+    __syncthreads();
+    kmin = s_kmin[0]; kmax = s_kmax[0]; nfin = s_nfin[0];
+    for (int w = 1; w < 8; ++w) { kmin = s_kmin[w] < kmin ? s_kmin[w] : kmin; kmax = s_kmax[w] > kmax ? s_kmax[w] : kmax; nfin += s_nfin[w]; }
+    if (nfin >= k && kmax >= kmin) {                                 // the k-th smallest is finite
+      const uint32_t diff = kmin ^ kmax;
+      hi_bit = diff ? 31 - __clz(diff) : -1;
+      mask = hi_bit >= 31 ? 0u : ~((2u << hi_bit) - 1u);             // hi_bit == -1 -> all bits fixed
+      if (hi_bit < 0) mask = 0xffffffffu;
+      if (threadIdx.x == 0) s_prefix = kmax & mask;
+    } else if (threadIdx.x == 0) {
+      s_prefix = 0u;
+    }
+  } else if (threadIdx.x == 0) {
+    s_prefix = 0u;
+  }
+  if (threadIdx.x == 0) s_remaining = (int)k;
+  __syncthreads();
+  while (hi_bit >= 0) {
+    const int lo_bit = hi_bit >= 7 ? hi_bit - 7 : 0;
+    const uint32_t dm = (1u << (hi_bit - lo_bit + 1)) - 1u;
     hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
     if (in_regs) {
 #pragma unroll
       for (int q = 0; q < KTH_MAXV; ++q)
-        if (threadIdx.x + 256 * q < n && (keys[q] & mask) == prefix) atomicAdd(&hist[(keys[q] >> shift) & 255u], 1);
+        if (threadIdx.x + 256 * q < n && (keys[q] & mask) == prefix) atomicAdd(&hist[(keys[q] >> lo_bit) & dm], 1);
     } else {
       for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
         const uint32_t key = order_key_f(rowp[j]);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> lo_bit) & dm], 1);
       }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       int rem = s_remaining, b = 0;
-      for (; b < 256; ++b) { if (hist[b] >= rem) break; rem -= hist[b]; }
+      for (; b < (int)dm; ++b) { if (hist[b] >= rem) break; rem -= hist[b]; }
       s_remaining = rem;
-      s_prefix = prefix | ((uint32_t)b << shift);
+      s_prefix = prefix | ((uint32_t)b << lo_bit);
     }
-    mask |= 255u << shift;
+    mask |= dm << lo_bit;
+    hi_bit = lo_bit - 1;
     __syncthreads();
   }
   const uint32_t tau = s_prefix;
