@@ -91,25 +91,15 @@ __global__ void __launch_bounds__(256) dist_blocks_kernel(const float* __restric
 }
 
 // One CTA per node (batch-global row): radix-select the k-th smallest (key, local index) of its row.
-// The row is read ONCE into registers (rows up to 256 * KTH_MAXV entries; longer rows re-read global).
-// With norm2 != nullptr (tensor-core Gram distances) the same pass also decides whether the row's top-k
-// SET is certain: ambiguous <=> an entry outside the top-k lies within the error band above the k-th
-// value (in d^2), band = beta * (||a_i||^2 + max_j ||a_j||^2).
-constexpr int KTH_MAXV = 20;
-
 __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restrict__ dense,
                                                             const int64_t* __restrict__ gptr, int64_t num_graphs,
                                                             const int64_t* __restrict__ doff, int64_t k,
                                                             const int32_t* __restrict__ row_mask,
                                                             uint32_t* __restrict__ thr_key,
-                                                            int32_t* __restrict__ thr_idx,
-                                                            const float* __restrict__ norm2,
-                                                            const float* __restrict__ win_nmax, float beta,
-                                                            int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
+                                                            int32_t* __restrict__ thr_idx) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining;
-  __shared__ float s_red[16];
   const int64_t i = blockIdx.x;
   if (row_mask != nullptr && row_mask[i] == 0) return;
   int64_t lo = 0, hi = num_graphs;                                  // window of node i
@@ -117,87 +107,31 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
   const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0;
   const float* rowp = dense + doff[lo] + (i - n0) * n;
   if (k >= n) {                                                     // every rank < k
-    if (threadIdx.x == 0) { thr_key[i] = 0xffffffffu; thr_idx[i] = (int32_t)n; if (amb != nullptr) amb[i] = 0; }
+    if (threadIdx.x == 0) { thr_key[i] = 0xffffffffu; thr_idx[i] = (int32_t)n; }
     return;
   }
-  const bool in_regs = n <= 256 * KTH_MAXV;
-  uint32_t keys[KTH_MAXV];
-#pragma unroll
-  for (int q = 0; q < KTH_MAXV; ++q) {
-    const int64_t j = threadIdx.x + 256 * q;
-    keys[q] = (in_regs && j < n) ? order_key_f(rowp[j]) : 0xffffffffu;
-  }
-  // Radix select over 8-bit digits.  Distances of one row share their leading bits (same exponent), so the
-  // digits above the highest bit in which the finite keys differ are skipped: fewer passes and, more
-  // importantly, a first histogram that is spread over its bins instead of one contended counter.
-  __shared__ uint32_t s_kmin[8], s_kmax[8];
-  __shared__ int s_nfin[8];
-  int hi_bit = 31;
+  if (threadIdx.x == 0) { s_prefix = 0u; s_remaining = (int)k; }
   uint32_t mask = 0u;
-  if (in_regs) {
-    uint32_t kmin = 0xffffffffu, kmax = 0u;
-    int nfin = 0;
-#pragma unroll
-    for (int q = 0; q < KTH_MAXV; ++q)
-      if (threadIdx.x + 256 * q < n && keys[q] < 0xff800000u) {      // finite, non-negative distance
-        kmin = keys[q] < kmin ? keys[q] : kmin;
-        kmax = keys[q] > kmax ? keys[q] : kmax;
-        ++nfin;
-      }
-    for (int d = 16; d > 0; d >>= 1) {
-      const uint32_t a = __shfl_xor_sync(kFullMask, kmin, d), b = __shfl_xor_sync(kFullMask, kmax, d);
-      kmin = a < kmin ? a : kmin;
-      kmax = b > kmax ? b : kmax;
-      nfin += __shfl_xor_sync(kFullMask, nfin, d);
-    }
-    if ((threadIdx.x & 31) == 0) { s_kmin[threadIdx.x >> 5] = kmin; s_kmax[threadIdx.x >> 5] = kmax; s_nfin[threadIdx.x >> 5] = nfin; }
-    __syncthreads();
-    kmin = s_kmin[0]; kmax = s_kmax[0]; nfin = s_nfin[0];
-    for (int w = 1; w < 8; ++w) { kmin = s_kmin[w] < kmin ? s_kmin[w] : kmin; kmax = s_kmax[w] > kmax ? s_kmax[w] : kmax; nfin += s_nfin[w]; }
-    if (nfin >= k && kmax >= kmin) {                                 // the k-th smallest is finite
-      const uint32_t diff = kmin ^ kmax;
-      hi_bit = diff ? 31 - __clz(diff) : -1;
-      mask = hi_bit >= 31 ? 0u : ~((2u << hi_bit) - 1u);             // hi_bit == -1 -> all bits fixed
-      if (hi_bit < 0) mask = 0xffffffffu;
-      if (threadIdx.x == 0) s_prefix = kmax & mask;
-    } else if (threadIdx.x == 0) {
-      s_prefix = 0u;
-    }
-  } else if (threadIdx.x == 0) {
-    s_prefix = 0u;
-  }
-  if (threadIdx.x == 0) s_remaining = (int)k;
-  __syncthreads();
-  while (hi_bit >= 0) {
-    const int lo_bit = hi_bit >= 7 ? hi_bit - 7 : 0;
-    const uint32_t dm = (1u << (hi_bit - lo_bit + 1)) - 1u;
+  for (int shift = 24; shift >= 0; shift -= 8) {
     hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
-    if (in_regs) {
-#pragma unroll
-      for (int q = 0; q < KTH_MAXV; ++q)
-        if (threadIdx.x + 256 * q < n && (keys[q] & mask) == prefix) atomicAdd(&hist[(keys[q] >> lo_bit) & dm], 1);
-    } else {
-      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-        const uint32_t key = order_key_f(rowp[j]);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> lo_bit) & dm], 1);
-      }
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      const uint32_t key = order_key_f(rowp[j]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       int rem = s_remaining, b = 0;
-      for (; b < (int)dm; ++b) { if (hist[b] >= rem) break; rem -= hist[b]; }
+      for (; b < 256; ++b) { if (hist[b] >= rem) break; rem -= hist[b]; }
       s_remaining = rem;
-      s_prefix = prefix | ((uint32_t)b << lo_bit);
+      s_prefix = prefix | ((uint32_t)b << shift);
     }
-    mask |= dm << lo_bit;
-    hi_bit = lo_bit - 1;
+    mask |= 255u << shift;
     __syncthreads();
   }
-  const uint32_t tau = s_prefix;
-  __shared__ int32_t s_found;
   if (threadIdx.x < 32) {                                           // ties: first `need` of them in index order
+    const uint32_t tau = s_prefix;
     const int need = s_remaining;
     const int lane = threadIdx.x;
     int seen = 0;
@@ -215,34 +149,7 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
       }
       seen += c;
     }
-    if (lane == 0) { thr_key[i] = tau; thr_idx[i] = found; s_found = found; }
-  }
-  if (norm2 == nullptr || amb == nullptr) return;
-  __syncthreads();
-  // ---- is the top-k set certain under the Gram error band?
-  const int32_t tfound = s_found;
-  float mn = INFINITY, nmax = win_nmax[lo];                          // max ||a_j||^2 over the window
-  auto visit = [&](uint32_t key, int64_t j) {
-    const bool outside = key > tau || (key == tau && j > tfound);
-    if (outside) { const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key; mn = fminf(mn, __uint_as_float(u)); }
-  };
-  if (in_regs) {
-#pragma unroll
-    for (int q = 0; q < KTH_MAXV; ++q) { const int64_t j = threadIdx.x + 256 * q; if (j < n) visit(keys[q], j); }
-  } else {
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) visit(order_key_f(rowp[j]), j);
-  }
-  for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, d));
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) mn = fminf(mn, s_red[q]);
-    const uint32_t u = (tau & 0x80000000u) ? (tau & 0x7fffffffu) : ~tau;
-    const float vk = __uint_as_float(u);
-    int flag = 0;
-    if (isfinite(vk) && isfinite(mn)) flag = (mn * mn - vk * vk) <= 2.f * beta * (norm2[i] + nmax) ? 1 : 0;
-    amb[i] = flag;
-    if (flag) atomicAdd(amb_count, 1);
+    if (lane == 0) { thr_key[i] = tau; thr_idx[i] = found; }
   }
 }
 
@@ -313,10 +220,10 @@ __global__ void graph_pair_ptr_kernel(const int64_t* __restrict__ gptr, int64_t 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim);
 int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
                      int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
-                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out,
-                     const float** win_nmax_out, cudaStream_t s);
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s);
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
-                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const int32_t* amb,
+                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
+                       const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
                        cudaStream_t s);
 
 }  // namespace mpn
@@ -364,14 +271,13 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   float* norm2 = nullptr;
   int32_t* amb = nullptr;
   int32_t* amb_count = nullptr;
-  const float* win_nmax = nullptr;
   int rc = MPN_OK;
   MPN_CUDA(cudaMemsetAsync(status, 0, 16, s));
 
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff); count_launch();
   if (tc) {
     rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
-                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, &win_nmax, s);
+                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, s);
     if (rc) return rc;
   } else {
     const int64_t nt = ceil_div(max_n, DT);
@@ -379,13 +285,12 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
     dist_blocks_kernel<<<grid, 256, 0, s>>>(reid, dim, frame, gptr, doff, max_frame_dist, dense); count_launch();
   }
   if (prune) {
-    batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti,
-                                                      tc ? norm2 : nullptr, win_nmax, 2e-6f, amb, amb_count); count_launch();
+    batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti); count_launch();
     if (tc) {                                                       // repair rows whose top-k set is not certain
-      rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, amb, s);
+      rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
+                              amb, amb_count, s);
       if (rc) return rc;
-      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti, nullptr, nullptr,
-                                                        0.f, nullptr, nullptr); count_launch();
+      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti); count_launch();
     }
   }
   const unsigned wgrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16);

@@ -32,8 +32,7 @@ __device__ __forceinline__ int slab_off(int n, int k16) {
 // warp per node: packed fp16 hi/lo image of its row inside its 128-row tile, ||a||^2 and sum(a).
 __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, const int64_t* __restrict__ gptr,
                                  int64_t num_graphs, const int64_t* __restrict__ tile_off, int64_t num_nodes,
-                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1,
-                                 int* __restrict__ win_nmax_bits) {
+                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -55,7 +54,7 @@ __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, co
       *reinterpret_cast<__half*>(base + (KC / 16) * SLAB) = l;
     }
     for (int d = 16; d > 0; d >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); }
-    if (lane == 0) { norm2[i] = s2; sum1[i] = s1; atomicMax(&win_nmax_bits[lo], __float_as_int(s2)); }   // s2 >= 0
+    if (lane == 0) { norm2[i] = s2; sum1[i] = s1; }
   }
 }
 
@@ -207,6 +206,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_blocks_kernel(GramArgs a) {
   if (warp == 0) tmem_dealloc<512>(*tmem_slot);
 }
 
+__device__ __forceinline__ uint32_t okey(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// One CTA per row: is the top-k SET of this row certain given the error band of the Gram distances?
+// ambiguous <=> an entry outside the top-k lies within the band above the k-th value (in d^2).
+__global__ void __launch_bounds__(256) row_ambiguity_kernel(const float* __restrict__ dense, const int64_t* __restrict__ gptr,
+                                                            int64_t num_graphs, const int64_t* __restrict__ doff,
+                                                            const float* __restrict__ norm2, const uint32_t* __restrict__ thr_key,
+                                                            const int32_t* __restrict__ thr_idx, float beta,
+                                                            int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
+  __shared__ float s_min[8];
+  __shared__ float s_nmax[8];
+  const int64_t i = blockIdx.x;
+  int64_t lo = 0, hi = num_graphs;
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
+  const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0;
+  const float* rowp = dense + doff[lo] + (i - n0) * n;
+  const uint32_t tk = thr_key[i];
+  const int32_t ti = thr_idx[i];
+  if (tk == 0xffffffffu) { if (threadIdx.x == 0) amb[i] = 0; return; }      // k >= row length: everything is in
+  float mn = INFINITY, nmax = 0.f;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const float v = rowp[j];
+    const uint32_t key = okey(v);
+    const bool outside = key > tk || (key == tk && j > ti);
+    if (outside) mn = fminf(mn, v);
+    nmax = fmaxf(nmax, norm2[n0 + j]);
+  }
+  for (int d = 16; d > 0; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, d)); }
+  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = mn; s_nmax[threadIdx.x >> 5] = nmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) { mn = fminf(mn, s_min[q]); nmax = fmaxf(nmax, s_nmax[q]); }
+    // k-th value from its key
+    const uint32_t u = (tk & 0x80000000u) ? (tk & 0x7fffffffu) : ~tk;
+    const float vk = __uint_as_float(u);
+    int flag = 0;
+    if (isfinite(vk) && isfinite(mn)) {
+      const float band = beta * (norm2[i] + nmax);                           // absolute error bound on d^2
+      flag = (mn * mn - vk * vk) <= 2.f * band ? 1 : 0;
+    }
+    amb[i] = flag;
+    if (flag) atomicAdd(amb_count, 1);
+  }
+}
+
 // Exact fp32 row (reference formula, sequential over the feature dimension) for the flagged rows.
 __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict__ reid, int64_t dim,
                                                          const int64_t* __restrict__ frame, const int64_t* __restrict__ gptr,
@@ -248,15 +295,14 @@ __global__ void tile_offsets_kernel(const int64_t* __restrict__ gptr, int64_t nu
 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim) {
   return align_up(total_tiles * (dim / gram::KC) * gram::CHUNK_BYTES, 256) + 2 * align_up(num_nodes * 4, 256) +
-         align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + align_up(num_graphs * 4, 256) + 1024;
+         align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + 1024;
 }
 
 // Fills the dense blocks with Gram distances, ranks, then repairs ambiguous rows exactly.
 // `rank_rows(mask)` is provided by knn_graph.cu (batch_row_kth_kernel launcher).
 int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
                      int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
-                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, const float** win_nmax_out,
-                     cudaStream_t s) {
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s) {
   using namespace gram;
   const int64_t n = h_gptr[num_graphs];
   int64_t total_tiles = 0, max_tiles = 0;
@@ -271,13 +317,11 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
   float* sum1 = cv.take<float>(n);
   int64_t* tile_off = cv.take<int64_t>(num_graphs + 1);
   int32_t* amb = cv.take<int32_t>(n + 1);
-  int* nmax_bits = cv.take<int>(num_graphs);
-  MPN_CUDA(cudaMemsetAsync(nmax_bits, 0, 4 * num_graphs, s));
   MPN_CUDA(cudaMemsetAsync(img, 0, total_tiles * (dim / KC) * CHUNK_BYTES, s));
   MPN_CUDA(cudaMemsetAsync(amb + n, 0, 4, s));
   tile_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, tile_off); count_launch();
   pack_reid_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16), 256, 0, s>>>(
-      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1, nmax_bits); count_launch();
+      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1); count_launch();
   static bool attr_set = false;
   if (!attr_set) {
     MPN_CUDA(cudaFuncSetAttribute(gram_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -294,14 +338,16 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
   gram_blocks_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a); count_launch();
   MPN_LAUNCH_CHECK();
   *norm2_out = norm2; *amb_out = amb; *amb_count_out = amb + n;
-  *win_nmax_out = reinterpret_cast<const float*>(nmax_bits);
   return MPN_OK;
 }
 
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
-                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const int32_t* amb,
+                       int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
+                       const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
                        cudaStream_t s) {
   using namespace gram;
+  row_ambiguity_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(dense, gptr, num_graphs, doff, norm2, thr_key, thr_idx, beta,
+                                                         amb, amb_count); count_launch();
   exact_rows_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(reid, dim, frame, gptr, num_graphs, doff, max_dist, amb, dense);
   count_launch();
   MPN_LAUNCH_CHECK();
