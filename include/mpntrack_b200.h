@@ -236,6 +236,36 @@ int64_t mpn_weighted_bce_workspace(void);
 int mpn_weighted_bce(const float* logits, const float* labels, int64_t steps, int64_t num_edges, float weight,
                      void* workspace, float* loss, float* pos_weight, float* grad, void* stream);
 
+/* ------------------------------------------------------------------ training building blocks
+ * pl_module/pl_module.py:122-135 (loss.backward(), Adam) for the core network, as deterministic fp32
+ * kernels (fixed-order reductions, no float atomics).  The Python layer (mpntrackseg_b200/training.py)
+ * composes them into the forward-with-activations and the backward of models/mpn.py:349-381. */
+
+/* C[m,n] = act(op(A) op(B) + bias) (+ C if accumulate).  op(A)(i,k) = trans_a ? a[k*lda+i] : a[i*lda+k],
+ * op(B)(k,j) = trans_b ? b[j*ldb+k] : b[k*ldb+j].  mask_a (may be NULL, same indexing as a with ldm): A is
+ * multiplied by (mask_a > 0), i.e. the ReLU backward of the tensor that produced the gradient in A. */
+int mpn_gemm(const float* a, int64_t lda, int trans_a, const float* mask_a, int64_t ldm, const float* b,
+             int64_t ldb, int trans_b, const float* bias, int relu, int accumulate, float* c, int64_t ldc,
+             int64_t m, int64_t n, int64_t k, void* stream);
+/* out[j] (+)= sum_i a[i*lda+j] * (mask == NULL || mask[i*ldm+j] > 0)   (bias gradients) */
+int mpn_colsum(const float* a, int64_t lda, const float* mask, int64_t ldm, int64_t m, int64_t n,
+               int accumulate, float* out, void* stream);
+/* out[r, col_off : col_off+width] = src[idx ? idx[r] : r, 0:width]   (torch.cat of gathered rows, models/mpn.py:69,86) */
+int mpn_gather_cols(const float* src, int64_t lds, int64_t width, const int32_t* idx, int64_t rows, float* out,
+                    int64_t ldo, int64_t col_off, void* stream);
+/* out[node, col_off+f] (+)= sum over q in [ptr[node], ptr[node+1]) of in[(perm ? perm[q] : q)*ld + in_off + f]
+ * in ascending q (scatter_add of models/mpn.py:89,96 and its transposes in the backward pass). */
+int mpn_segment_sum(const float* in, int64_t ld, int64_t in_off, int64_t width, const int32_t* ptr,
+                    const int32_t* perm, int64_t nodes, int accumulate, float* out, int64_t ldo,
+                    int64_t col_off, void* stream);
+/* g[i] = y[i] > 0 ? g[i] : 0 */
+int mpn_relu_mask(float* g, const float* y, int64_t n, void* stream);
+/* torch.optim.Adam step (configs/tracking_cfg.yaml:6-10: lr 1e-3, weight_decay 1e-4 as L2 term) on flat
+ * buffers; grads are multiplied by grad_scale first (1/world_size after a summed all-reduce). */
+int mpn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  void* stream);
+
 /* Same contract as mpn_mp_forward (num_steps >= 1), evaluated on the tcgen05 tensor cores:
  * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).

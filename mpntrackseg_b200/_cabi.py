@@ -64,6 +64,13 @@ SIGNATURES = {
                               c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_mp_forward': (C.c_int, [C.POINTER(CoreWeights), C.POINTER(EdgeLayout), c_vp, c_vp, c_i32, c_i32,
                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'mpn_gemm': (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_i64,
+                           c_i64, c_i64, c_i64, c_vp]),
+    'mpn_colsum': (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    'mpn_gather_cols': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    'mpn_segment_sum': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_i64, c_vp]),
+    'mpn_relu_mask': (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    'mpn_adam_step': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
     'mpn_weighted_bce_workspace': (c_i64, []),
     'mpn_weighted_bce': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_attn_aggregate': (C.c_int, [c_vp, c_i64, c_i64, C.POINTER(EdgeLayout), c_vp, c_vp, c_vp, c_vp]),

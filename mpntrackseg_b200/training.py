@@ -1,0 +1,263 @@
+"""Training step of the core network on the GPU: forward with stored activations, weighted-BCE
+loss over the classified steps, hand-written backward, gradient all-reduce and Adam.
+
+reference: pl_module/pl_module.py:88-135 (_compute_loss, _train_val_step), scripts/train.py:65-77
+(Adam lr 1e-3 / weight_decay 1e-4, accumulate_grad_batches 8 -- here 8 ranks with one graph each and
+one summed all-reduce of a single flat gradient bucket), models/mpn.py:349-381 for the forward.
+
+The arithmetic runs in the deterministic fp32 kernels of csrc/train_ops.cu (mpn_gemm, mpn_colsum,
+mpn_gather_cols, mpn_segment_sum, mpn_adam_step) and csrc/loss.cu; torch only owns the buffers, does
+index bookkeeping (argsort of the column indices) and trivial elementwise adds of gradient buffers.
+Scope: the tracking loss of the core network (encoders, MPNet, classifier).  The mask branch / mask loss
+are not trained here.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from ._cabi import check, lib, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------ thin wrappers
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError('expected a 2-D tensor with unit column stride')
+    return t.stride(0)
+
+
+def gemm(a, b, ta=False, tb=False, bias=None, relu=False, mask=None, out=None, accumulate=False):
+    """out = act(op(a) @ op(b) + bias) (+ out).  mask: a is multiplied by (mask > 0) elementwise."""
+    m = a.shape[1] if ta else a.shape[0]
+    k = a.shape[0] if ta else a.shape[1]
+    n = b.shape[0] if tb else b.shape[1]
+    kb = b.shape[1] if tb else b.shape[0]
+    if k != kb:
+        raise ValueError(f'gemm: inner sizes differ ({k} vs {kb})')
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    check(lib().mpn_gemm(ptr(a), _ld(a), int(ta), ptr(mask), _ld(mask) if mask is not None else 0, ptr(b), _ld(b), int(tb),
+                         ptr(bias), int(relu), int(accumulate), ptr(out), _ld(out), m, n, k, stream_ptr()), 'gemm')
+    return out
+
+
+def colsum(a, mask=None, out=None, accumulate=False):
+    m, n = a.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=a.device)
+    check(lib().mpn_colsum(ptr(a), _ld(a), ptr(mask), _ld(mask) if mask is not None else 0, m, n, int(accumulate),
+                           ptr(out), stream_ptr()), 'colsum')
+    return out
+
+
+def gather_cols(src, idx, out, col_off):
+    rows = out.shape[0]
+    check(lib().mpn_gather_cols(ptr(src), _ld(src), src.shape[1], ptr(idx), rows, ptr(out), _ld(out), col_off,
+                                stream_ptr()), 'gather_cols')
+
+
+def segment_sum(inp, in_off, width, seg_ptr, perm, out, col_off, accumulate=False):
+    check(lib().mpn_segment_sum(ptr(inp), _ld(inp), in_off, width, ptr(seg_ptr), ptr(perm), out.shape[0], int(accumulate),
+                                ptr(out), _ld(out), col_off, stream_ptr()), 'segment_sum')
+
+
+class _Linear:
+    """y = act(x W^T + b) with its backward (ReLU folded in through the output mask)."""
+
+    def __init__(self, w, b, relu, gw, gb):
+        self.w, self.b, self.relu, self.gw, self.gb = w, b, relu, gw, gb
+
+    def fwd(self, x):
+        return gemm(x, self.w, tb=True, bias=self.b, relu=self.relu)
+
+    def bwd(self, x, y, gy, need_gx=True):
+        mask = y if self.relu else None
+        gemm(gy, x, ta=True, mask=mask, out=self.gw, accumulate=True)         # gW += (gy*[y>0])^T x
+        colsum(gy, mask=mask, out=self.gb, accumulate=True)
+        return gemm(gy, self.w, mask=mask) if need_gx else None               # gx = (gy*[y>0]) W
+
+
+CORE_PREFIXES = ('encoder.', 'classifier.', 'MPNet.')
+
+
+class CoreTrainer:
+    """Owns a flat parameter / gradient / Adam-state bucket for the core network of a ``MOTMPNet``."""
+
+    def __init__(self, model, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.named = OrderedDict((n, p) for n, p in model.named_parameters() if n.startswith(CORE_PREFIXES))
+        dev = next(iter(self.named.values())).device
+        total = sum(p.numel() for p in self.named.values())
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.g = OrderedDict()
+        off = 0
+        for n, p in self.named.items():                      # parameters become views of the flat bucket
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            self.g[n] = self.grad[off:off + k].view_as(p)
+            off += k
+        self.lr, self.weight_decay, self.betas, self.eps, self.t = lr, weight_decay, betas, eps, 0
+
+    # ---------------------------------------------------------------- helpers
+    def _lin(self, prefix, slot, relu):
+        w, b = self.named[f'{prefix}.{slot}.weight'], self.named[f'{prefix}.{slot}.bias']
+        return _Linear(w.data, b.data, relu, self.g[f'{prefix}.{slot}.weight'], self.g[f'{prefix}.{slot}.bias'].view(-1))
+
+    def _mlp(self, prefix):
+        slots = sorted({int(n[len(prefix) + 1:].split('.')[1]) for n in self.named
+                        if n.startswith(prefix + '.fc_layers.') and n.endswith('.weight')})
+        return [self._lin(prefix + '.fc_layers', s, self.named[f'{prefix}.fc_layers.{s}.weight'].shape[0] != 1)
+                for s in slots]
+
+    # ---------------------------------------------------------------- forward + backward
+    def loss_and_grads(self, data, edge_labels, tracking_weight=1.0, zero_grad=True):
+        """Forward (models/mpn.py:349-381), loss (pl_module.py:88-105) and backward of the core network for
+        one graph (or block-diagonal batch).  Gradients are ACCUMULATED into ``self.g`` (zeroed first
+        unless zero_grad=False).  Returns the loss as a 1-element device tensor."""
+        m = self.model
+        if zero_grad:
+            self.grad.zero_()
+        x = data.x
+        pooled = ops.avgpool(x) if x.dim() > 2 else x.contiguous()
+        n = pooled.shape[0]
+        lay = ops.edge_layout(data.edge_index, n)
+        e = lay.num_edges
+        srow, scol, sedge = lay.slot_row[:e], lay.slot_col[:e], lay.slot_edge[:e]
+        order = torch.argsort(scol, stable=True)                         # slots grouped by column (index bookkeeping)
+        perm_c = order.to(torch.int32)
+        ptr_c = torch.zeros(n + 1, dtype=torch.int32, device=pooled.device)
+        ptr_c[1:] = torch.cumsum(torch.bincount(scol.long(), minlength=n), 0).to(torch.int32)
+        dev = pooled.device
+        steps, first_cls = m.num_enc_steps, m.num_enc_steps - m.num_class_steps + 1
+        n_out = lay.num_out
+
+        enc_n, enc_e = self._mlp('encoder.node_model'), self._mlp('encoder.edge_model')
+        edge_mlp = self._mlp('MPNet.edge_model.edge_model')
+        flow = {'out': self._mlp('MPNet.node_model.flow_out_model'), 'in': self._mlp('MPNet.node_model.flow_in_model')}
+        node_lin = self._lin('MPNet.node_model.node_model', 0, True)
+        cls = self._mlp('classifier.edge_model')
+        dn, de = node_lin.w.shape[0], edge_mlp[-1].w.shape[0]
+        fh = flow['out'][0].w.shape[0]
+
+        # ---- encoders (activations kept)
+        acts_n = [pooled]
+        for l in enc_n:
+            acts_n.append(l.fwd(acts_n[-1]))
+        x0 = acts_n[-1]
+        acts_e = [ops.gather_rows(data.edge_attr.contiguous(), sedge) if e else data.edge_attr.new_empty((0, 6))]
+        for l in enc_e:
+            acts_e.append(l.fwd(acts_e[-1]))
+        e0 = acts_e[-1]
+
+        # ---- message-passing steps
+        xs, es, saved, logits = x0, e0, [], []
+        ranges = (('out', 0, n_out, dn), ('in', n_out, e, 0))            # (name, slot range, column offset in [flow_in|flow_out])
+        for step in range(1, steps + 1):
+            a = torch.empty((e, 4 * dn + 2 * de), dtype=torch.float32, device=dev)
+            gather_cols(x0, srow, a, 0); gather_cols(xs, srow, a, dn)
+            gather_cols(x0, scol, a, 2 * dn); gather_cols(xs, scol, a, 3 * dn)
+            gather_cols(e0, None, a, 4 * dn); gather_cols(es, None, a, 4 * dn + de)
+            h = edge_mlp[0].fwd(a)
+            e2 = edge_mlp[1].fwd(h)
+            c1 = cls[0].fwd(e2)
+            lg = cls[1].fwd(c1)
+            b = torch.empty((e, 2 * dn + de), dtype=torch.float32, device=dev)
+            gather_cols(a[:, 2 * dn:4 * dn], None, b, 0); gather_cols(e2, None, b, 2 * dn)
+            g_ = torch.empty((e, fh), dtype=torch.float32, device=dev)
+            msg = torch.empty((e, dn), dtype=torch.float32, device=dev)
+            f = torch.empty((n, 2 * dn), dtype=torch.float32, device=dev)
+            for name, s0, s1, coff in ranges:
+                if s1 > s0:
+                    gemm(b[s0:s1], flow[name][0].w, tb=True, bias=flow[name][0].b, relu=True, out=g_[s0:s1])
+                    gemm(g_[s0:s1], flow[name][1].w, tb=True, bias=flow[name][1].b, relu=True, out=msg[s0:s1])
+                segment_sum(msg, 0, dn, lay.out_ptr if name == 'out' else lay.in_ptr, None, f, coff)
+            xs_new = node_lin.fwd(f)
+            saved.append((a, h, e2, c1, b, g_, msg, f, xs_new))
+            if step >= first_cls:
+                logits.append(lg.view(-1))
+            xs, es = xs_new, e2
+        if steps == 0:
+            raise NotImplementedError('training with num_enc_steps == 0')
+
+        # ---- loss (slot order on both sides) and its gradient w.r.t. the logits
+        labels = edge_labels.to(dev, torch.float32).reshape(-1)[sedge.long()].contiguous()
+        lg_all = torch.stack(logits)
+        loss, _, g_logits = ops.weighted_bce(lg_all, labels, weight=tracking_weight, want_grad=True)
+
+        # ---- backward through the steps
+        gxs = torch.zeros((n, dn), dtype=torch.float32, device=dev)
+        ge2_next = torch.zeros((e, de), dtype=torch.float32, device=dev)
+        gx0 = torch.zeros((n, dn), dtype=torch.float32, device=dev)
+        ge0 = torch.zeros((e, de), dtype=torch.float32, device=dev)
+        for step in range(steps, 0, -1):
+            a, h, e2, c1, b, g_, msg, f, xs_new = saved[step - 1]
+            gf = node_lin.bwd(f, xs_new, gxs)                                           # [n, 2dn]
+            gmsg = torch.empty((e, dn), dtype=torch.float32, device=dev)
+            gb = torch.empty((e, 2 * dn + de), dtype=torch.float32, device=dev)
+            for name, s0, s1, coff in ranges:
+                if s1 <= s0:
+                    continue
+                gather_cols(gf[:, coff:coff + dn], srow[s0:s1], gmsg[s0:s1], 0)       # d flow[row] -> each message
+                l0, l1 = flow[name]
+                gg = l1.bwd(g_[s0:s1], msg[s0:s1], gmsg[s0:s1])
+                gemm(gg, b[s0:s1], ta=True, mask=g_[s0:s1], out=l0.gw, accumulate=True)
+                colsum(gg, mask=g_[s0:s1], out=l0.gb, accumulate=True)
+                gemm(gg, l0.w, mask=g_[s0:s1], out=gb[s0:s1])
+            ge2 = ge2_next + gb[:, 2 * dn:]                                             # e' feeds the flow MLPs and step+1
+            if step >= first_cls:
+                gl = g_logits[step - first_cls].view(-1, 1)
+                gc1 = cls[1].bwd(c1, None, gl)
+                gemm(gc1, e2, ta=True, mask=c1, out=cls[0].gw, accumulate=True)
+                colsum(gc1, mask=c1, out=cls[0].gb, accumulate=True)
+                gemm(gc1, cls[0].w, mask=c1, out=ge2, accumulate=True)
+            gh = edge_mlp[1].bwd(h, e2, ge2)
+            ga = edge_mlp[0].bwd(a, h, gh)                                              # [e, 4dn+2de]
+            gxs_new = torch.empty((n, dn), dtype=torch.float32, device=dev)
+            for part, dst in ((0, gx0), (dn, gxs_new)):                                 # x_init part / x_latent part
+                acc = dst is gx0
+                segment_sum(ga, part, dn, lay.out_ptr, None, dst, 0, accumulate=acc)                 # x[row], flow_out group
+                segment_sum(ga, part, dn, lay.in_ptr, None, dst, 0, accumulate=True)                 # x[row], flow_in group
+                segment_sum(ga, 2 * dn + part, dn, ptr_c, perm_c, dst, 0, accumulate=True)           # x[col] of the edge MLP
+                segment_sum(gb, part, dn, ptr_c, perm_c, dst, 0, accumulate=True)                    # x[col] of the flow MLPs
+            ge0 += ga[:, 4 * dn:4 * dn + de]
+            ge2_next = ga[:, 4 * dn + de:].contiguous()
+            gxs = gxs_new
+        gx0 += gxs                                                       # before step 1 the latent states are the
+        ge0 += ge2_next                                                  # initial encodings (models/mpn.py:358-359)
+
+        # ---- encoders
+        g_act = gx0
+        for i in range(len(enc_n) - 1, -1, -1):
+            g_act = enc_n[i].bwd(acts_n[i], acts_n[i + 1], g_act, need_gx=i > 0)
+        g_act = ge0
+        for i in range(len(enc_e) - 1, -1, -1):
+            g_act = enc_e[i].bwd(acts_e[i], acts_e[i + 1], g_act, need_gx=i > 0)
+        return loss
+
+    # ---------------------------------------------------------------- optimizer
+    def all_reduce_grads(self, group=None):
+        """One summed all-reduce of the single flat gradient bucket (1.19 MB); NCCL on GPUs."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    def adam_step(self, grad_scale=1.0):
+        self.t += 1
+        check(lib().mpn_adam_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.flat.numel(),
+                                  float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                  float(self.weight_decay), int(self.t), float(grad_scale), stream_ptr()), 'adam_step')
+
+    def train_step(self, data, edge_labels, tracking_weight=1.0, group=None):
+        """loss.backward() + gradient all-reduce (mean over ranks) + Adam, as Lightning drives it
+        (pl_module.py:137-141, scripts/train.py:76 with the 8 accumulated batches spread over 8 ranks)."""
+        loss = self.loss_and_grads(data, edge_labels, tracking_weight)
+        world = self.all_reduce_grads(group)
+        self.adam_step(grad_scale=1.0 / world)
+        return loss

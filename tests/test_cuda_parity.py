@@ -497,3 +497,65 @@ def test_tensor_core_gram_config2_window_no_repairs_needed():
     ex = build_window_graphs(inp, ds, fps=30.0, engine='fp32')
     assert torch.equal(tc.edge_index, ex.edge_index)
     assert repaired <= w.N // 20, repaired                  # well-separated data: (almost) nothing to repair
+
+
+def _oracle_loss_and_grads(P, mp, x, ei, ea, labels, weight):
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    out = mpn_ref.mpn_forward(Pg, mp, x, ei, ea)
+    loss = mpn_ref.weighted_bce_loss(out['classified_edges'], labels, tracking_weight=weight)
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in Pg.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize('name', ['tiny_nonrecip', 'kitti_shape'])
+def test_training_backward_matches_autograd_of_the_oracle(name):
+    """Hand-written backward (csrc/train_ops.cu, training.py) of the core network + weighted BCE against
+    torch autograd through the CPU oracle on the same graph, weights and labels."""
+    from mpntrackseg_b200.training import CoreTrainer
+    c = load_case(name)
+    win, gold, mp = c['win'], c['gold'], c['mp']
+    P = {k: v for k, v in c['P'].items() if k.startswith(('encoder.', 'classifier.', 'MPNet.'))}
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    labels = (win.ident[ei[0]] == win.ident[ei[1]]).float()
+    assert 0 < labels.sum() < labels.numel()
+    ref_loss, ref_g = _oracle_loss_and_grads(P, mp, win.x, ei, ea, labels, 0.8)
+    model = make_model(mp, c['P'], 'fp32')
+    tr = CoreTrainer(model)
+    data = Data()
+    data.x, data.edge_index, data.edge_attr = win.x.to(dev()), ei.to(dev()), ea.to(dev())
+    loss = tr.loss_and_grads(data, labels.to(dev()), tracking_weight=0.8)
+    assert abs(float(loss) - ref_loss) <= 2e-4 * max(1.0, abs(ref_loss))
+    assert set(tr.g) == set(ref_g)
+    for k, g in ref_g.items():
+        got = tr.g[k].cpu()
+        scale = float(g.abs().max()) + 1e-12
+        err = float((got - g).abs().max()) / scale
+        assert err <= 2e-3, (k, err, scale)
+    # two identical passes -> bit-identical gradients (deterministic reductions)
+    g1 = tr.grad.clone()
+    tr.loss_and_grads(data, labels.to(dev()), tracking_weight=0.8)
+    assert torch.equal(g1, tr.grad)
+
+
+def test_adam_step_matches_torch_adam():
+    from mpntrackseg_b200.training import CoreTrainer
+    c = load_case('tiny_nonrecip')
+    win, gold, mp = c['win'], c['gold'], c['mp']
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    labels = (win.ident[ei[0]] == win.ident[ei[1]]).float()
+    model = make_model(mp, c['P'], 'fp32')
+    tr = CoreTrainer(model, lr=1e-3, weight_decay=1e-4)
+    data = Data()
+    data.x, data.edge_index, data.edge_attr = win.x.to(dev()), ei.to(dev()), ea.to(dev())
+    ref_p = [p.detach().clone().requires_grad_(True) for p in tr.named.values()]
+    opt = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-4)
+    for _ in range(3):
+        tr.loss_and_grads(data, labels.to(dev()))
+        for rp, g in zip(ref_p, tr.g.values()):
+            rp.grad = g.detach().clone()
+        opt.step()
+        tr.adam_step()
+    for rp, p in zip(ref_p, tr.named.values()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), rp.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
