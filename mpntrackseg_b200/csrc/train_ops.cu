@@ -20,19 +20,22 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
                                                    const float* __restrict__ mask_a, int64_t ldm,
                                                    const float* __restrict__ b, int64_t ldb, int tb,
                                                    const float* __restrict__ bias, int relu, int accumulate,
-                                                   float* __restrict__ c, int64_t ldc, int64_t m, int64_t n, int64_t k) {
+                                                   float* __restrict__ c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                                                   int64_t k_per_split, float* __restrict__ partial) {
   __shared__ float As[GK][GT + 4];
   __shared__ float Bs[GK][GT + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t m0 = (int64_t)blockIdx.y * GT, n0 = (int64_t)blockIdx.x * GT;
+  const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+  const int64_t kend = kbeg + k_per_split < k ? kbeg + k_per_split : k;
   float acc[4][4] = {};
-  for (int64_t k0 = 0; k0 < k; k0 += GK) {
+  for (int64_t k0 = kbeg; k0 < kend; k0 += GK) {
     for (int idx = threadIdx.x; idx < GT * GK; idx += 256) {
       int r, kk;
       if (ta) { r = idx % GT; kk = idx / GT; } else { r = idx / GK; kk = idx % GK; }   // coalesced along the contiguous dim
       const int64_t gm = m0 + r, gk = k0 + kk;
       float v = 0.f;
-      if (gm < m && gk < k) {
+      if (gm < m && gk < kend) {
         v = ta ? a[gk * lda + gm] : a[gm * lda + gk];
         if (mask_a != nullptr) v = (ta ? mask_a[gk * ldm + gm] : mask_a[gm * ldm + gk]) > 0.f ? v : 0.f;
       }
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
       int r, kk;
       if (tb) { r = idx / GK; kk = idx % GK; } else { r = idx % GT; kk = idx / GT; }
       const int64_t gn = n0 + r, gk = k0 + kk;
-      Bs[kk][r] = (gn < n && gk < k) ? (tb ? b[gn * ldb + gk] : b[gk * ldb + gn]) : 0.f;
+      Bs[kk][r] = (gn < n && gk < kend) ? (tb ? b[gn * ldb + gk] : b[gk * ldb + gn]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
     for (int j = 0; j < 4; ++j) {
       const int64_t gn = n0 + tx * 4 + j;
       if (gn >= n) continue;
+      if (partial != nullptr) { partial[((int64_t)blockIdx.z * m + gm) * n + gn] = acc[i][j]; continue; }
       float v = acc[i][j] + (bias != nullptr ? bias[gn] : 0.f);
       if (accumulate) v += c[gm * ldc + gn];
       c[gm * ldc + gn] = relu ? fmaxf(v, 0.f) : v;
@@ -72,15 +76,30 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
   }
 }
 
-// column sums of (A .* (mask > 0)) -> out[n] (+)= ...; one CTA per 32 columns, rows walked in order
+// c = act(sum_z partial[z] + bias) (+ c): the split-K slices are added in ascending z (deterministic)
+__global__ void gemm_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias, int relu,
+                                   int accumulate, float* __restrict__ c, int64_t ldc, int64_t m, int64_t n) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m * n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gm = t / n, gn = t - gm * n;
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += partial[(int64_t)z * m * n + t];
+    v += bias != nullptr ? bias[gn] : 0.f;
+    if (accumulate) v += c[gm * ldc + gn];
+    c[gm * ldc + gn] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+// column sums of (A .* (mask > 0)) -> out[n] (+)= ...; one CTA per 32 columns, rows walked in a fixed order
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, int64_t lda,
                                                      const float* __restrict__ mask, int64_t ldm, int64_t m,
-                                                     int64_t n, int accumulate, float* __restrict__ out) {
+                                                     int64_t n, int64_t rows_per_slice, float* __restrict__ partial) {
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), rgrp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t r1 = r0 + rows_per_slice < m ? r0 + rows_per_slice : m;
   float s = 0.f;
   if (col < n)
-    for (int64_t r = rgrp; r < m; r += 8) {
+    for (int64_t r = r0 + rgrp; r < r1; r += 8) {
       float v = a[r * lda + col];
       if (mask != nullptr && !(mask[r * ldm + col] > 0.f)) v = 0.f;
       s += v;
@@ -90,7 +109,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a
   if (rgrp == 0 && col < n) {
     float t = 0.f;
     for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x & 31];
-    out[col] = accumulate ? out[col] + t : t;
+    partial[(int64_t)blockIdx.y * n + col] = t;
+  }
+}
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int slices, int64_t n, int accumulate,
+                                     float* __restrict__ out) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int y = 0; y < slices; ++y) t += partial[(int64_t)y * n + c];     // ascending slices: deterministic
+    out[c] = accumulate ? out[c] + t : t;
   }
 }
 
@@ -134,6 +162,18 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+static void keep_async_pool() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done = true;
+}
+
 static inline unsigned flat_grid(int64_t n) {
   return (unsigned)std::min<int64_t>(ceil_div(n > 0 ? n : 1, 256), (int64_t)sm_count() * 8);
 }
@@ -150,10 +190,33 @@ int mpn_gemm(const float* a, int64_t lda, int trans_a, const float* mask_a, int6
   MPN_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "gemm: negative size");
   if (m == 0 || n == 0) return MPN_OK;
   MPN_CHECK_ARG(c != nullptr && (k == 0 || (a && b)), "gemm: null pointer");
-  dim3 grid((unsigned)ceil_div(n, GT), (unsigned)ceil_div(m, GT));
-  gemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, lda, trans_a, mask_a, ldm, b, ldb, trans_b, bias, relu, accumulate, c,
-                                                  ldc, m, n, k);
-  count_launch();
+  cudaStream_t s = as_stream(stream);
+  keep_async_pool();
+  const int64_t tiles = ceil_div(n, GT) * ceil_div(m, GT);
+  // few output tiles but a long contraction (weight gradients: contraction over the edges): split K
+  int64_t splits = 1;
+  if (tiles < 2 * sm_count() && k >= 2048) {
+    splits = std::min<int64_t>(ceil_div(4 * (int64_t)sm_count(), tiles), ceil_div(k, 512));
+    if (splits > 256) splits = 256;
+  }
+  if (splits <= 1) {
+    dim3 grid((unsigned)ceil_div(n, GT), (unsigned)ceil_div(m, GT), 1);
+    gemm_kernel<<<grid, 256, 0, s>>>(a, lda, trans_a, mask_a, ldm, b, ldb, trans_b, bias, relu, accumulate, c, ldc, m, n, k,
+                                     k, nullptr);
+    count_launch();
+  } else {
+    const int64_t kps = align_up(ceil_div(k, splits), GK);
+    splits = ceil_div(k, kps);
+    float* partial = nullptr;
+    MPN_CUDA(cudaMallocAsync(&partial, sizeof(float) * splits * m * n, s));
+    dim3 grid((unsigned)ceil_div(n, GT), (unsigned)ceil_div(m, GT), (unsigned)splits);
+    gemm_kernel<<<grid, 256, 0, s>>>(a, lda, trans_a, mask_a, ldm, b, ldb, trans_b, nullptr, 0, 0, c, ldc, m, n, k, kps,
+                                     partial);
+    count_launch();
+    gemm_reduce_kernel<<<flat_grid(m * n), 256, 0, s>>>(partial, (int)splits, bias, relu, accumulate, c, ldc, m, n);
+    count_launch();
+    MPN_CUDA(cudaFreeAsync(partial, s));
+  }
   MPN_LAUNCH_CHECK();
   return MPN_OK;
 }
@@ -162,8 +225,18 @@ int mpn_colsum(const float* a, int64_t lda, const float* mask, int64_t ldm, int6
                float* out, void* stream) {
   if (n == 0) return MPN_OK;
   MPN_CHECK_ARG(out != nullptr && (m == 0 || a != nullptr), "colsum: null pointer");
-  colsum_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, as_stream(stream)>>>(a, lda, mask, ldm, m, n, accumulate, out);
+  cudaStream_t s = as_stream(stream);
+  keep_async_pool();
+  const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(ceil_div(m, 256), 128));
+  const int64_t rps = ceil_div(m > 0 ? m : 1, slices);
+  float* partial = nullptr;
+  MPN_CUDA(cudaMallocAsync(&partial, sizeof(float) * slices * n, s));
+  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)slices);
+  colsum_kernel<<<grid, 256, 0, s>>>(a, lda, mask, ldm, m, n, rps, partial);
   count_launch();
+  colsum_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(partial, (int)slices, n, accumulate, out);
+  count_launch();
+  MPN_CUDA(cudaFreeAsync(partial, s));
   MPN_LAUNCH_CHECK();
   return MPN_OK;
 }
