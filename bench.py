@@ -44,6 +44,9 @@ def parse():
     ap.add_argument('--k', type=int, default=50)
     ap.add_argument('--pooled', action='store_true', help='node features already pooled [N,2048]')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="'train': BASELINE configs[3] -- KITTI-shaped training step (fwd+bwd, 12 MP steps, 11 classified) "
+                         'with one NCCL all-reduce of the flat gradient bucket + Adam; extra to the headline contract')
     return ap.parse_args()
 
 
@@ -363,9 +366,77 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ training config (BASELINE configs[3])
+def run_train(a):
+    import torch.distributed as dist
+    from mpntrackseg_b200 import _cabi
+    from mpntrackseg_b200.data.mot_graph import MOTGraph
+    from mpntrackseg_b200.models.mpn import MOTMPNet
+    from mpntrackseg_b200.sharding import reduce_step_stats
+    from mpntrackseg_b200.training import CoreTrainer
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ds = default_dataset_params(top_k_nns=100, frames_per_graph=20)
+    mp = default_graph_model_params(NUM_STEPS_MP, NUM_CLASS_STEPS)
+    P = synth.make_params(mp, seed=6, gain=0.95, core_only=True)
+    model = MOTMPNet(mp).to(dev)
+    model.load_state_dict(P, strict=False)
+    tr = CoreTrainer(model)
+    w = synth.make_window(T=20, D=8, k=100, seed=100 + rank)
+    g = MOTGraph(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': w.fps}, ds).construct_graph_object()
+    ident = w.ident.to(dev)
+    labels = (ident[g.edge_index[0]] == ident[g.edge_index[1]]).float()
+    lib = _cabi.lib()
+    for _ in range(a.warmup):
+        tr.train_step(g, labels)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = lib.mpn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.train_step(g, labels)
+    e1.record()
+    torch.cuda.synchronize()
+    ms, (edges,) = reduce_step_stats(e0.elapsed_time(e1), [g.edge_index.shape[1]], device=dev)
+    if rank == 0:
+        line = dict(metric='edge-updates/s (training step: fwd+bwd+all-reduce+Adam)', value=NUM_STEPS_MP * edges * a.steps / (ms * 1e-3),
+                    unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                    config={'workload': 'configs[3]: KITTI-shaped window T=20 D=8 k=100 per GPU, 12 MP steps, 11 classified, '
+                                        'weighted BCE, one summed all-reduce of the 1.19 MB gradient bucket, Adam',
+                            'edges_per_gpu': int(g.edge_index.shape[1]), 'nodes_per_gpu': int(w.N)},
+                    gpu_launches=int(lib.mpn_launch_count() - l0), loss=float(loss))
+        if not a.no_cpu_baseline and world == 1:
+            from oracle import graph_ref, mpn_ref
+            torch.set_num_threads(os.cpu_count() or 1)
+            rg = graph_ref.build_graph(w.frame, w.reid, synth.det_columns(w), w.fps, ds)
+            lab = (w.ident[rg['edge_index'][0]] == w.ident[rg['edge_index'][1]]).float()
+            Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+            def cpu_step():
+                out = mpn_ref.mpn_forward(Pg, mp, w.x, rg['edge_index'], rg['edge_attr'])
+                mpn_ref.weighted_bce_loss(out['classified_edges'], lab).backward()
+            cpu_step()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                cpu_step()
+            dt = (time.perf_counter() - t0) / 3
+            line['cpu_baseline'] = dict(value=NUM_STEPS_MP * rg['edge_index'].shape[1] / dt, unit=UNIT, cores=os.cpu_count(), kind='port',
+                                        sample=f'3 x fwd+bwd (autograd) of the same window on the oracle, {dt * 1e3:.0f} ms each')
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     args = parse()
-    if args.impl == 'reference':
+    if args.mode == 'train' and args.impl != 'reference':
+        run_train(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_b200(args)

@@ -36,7 +36,12 @@ def fresh():
 
 tr = fresh()
 g, labels = window(100 + rank)
-for it in range(3):
+# first step by hand to keep the all-reduced gradient bucket for the comparison below
+tr.loss_and_grads(g, labels)
+tr.all_reduce_grads()
+grad_ddp = tr.grad.clone()
+tr.adam_step(grad_scale=1.0 / world)
+for it in range(2):
     loss = tr.train_step(g, labels)
 torch.cuda.synchronize()
 if world > 1:
@@ -49,15 +54,20 @@ dt = (time.perf_counter() - t0) / 10
 if rank == 0:
     ref = fresh()
     graphs = [window(100 + r) for r in range(world)]
+    gerr = None
     for it in range(13):
         ref.grad.zero_()
         for gg, ll in graphs:
             ref.loss_and_grads(gg, ll, zero_grad=False)
+        if gerr is None:
+            gerr = float((ref.grad - grad_ddp).abs().max()) / float(ref.grad.abs().max())
         ref.adam_step(grad_scale=1.0 / world)
     err = float((ref.flat - tr.flat).abs().max()) / float(ref.flat.abs().max())
     e = g.edge_index.shape[1]
     print(f'world={world} E={e} train step {dt * 1e3:.2f} ms  ({12 * e * world / dt / 1e6:.1f} M edge-updates/s fwd+bwd)  '
-          f'loss={float(loss):.5f}  max rel param diff vs single-process replay = {err:.2e}')
-    assert err < 1e-4, err
+          f'loss={float(loss):.5f}  all-reduced gradient vs single-process sum: {gerr:.2e}; params after 13 Adam steps: {err:.2e}')
+    # gradients agree to fp32 summation order; Adam amplifies noise-level gradients of dead units (update = +-lr),
+    # so the parameter comparison is loose
+    assert gerr < 1e-5 and err < 5e-3, (gerr, err)
 if world > 1:
     dist.destroy_process_group()
