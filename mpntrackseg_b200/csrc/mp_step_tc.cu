@@ -24,11 +24,16 @@
 // them to the group's mbarrier; while one group runs an epilogue the tensor core runs the other
 // group's layer.  Operand rows of the next tile are staged with cp.async during the current one,
 // the per-row message sums of the previous tile run under the current tile's first layer.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace mpn {
 namespace tc {
+
+int variant();   // 2: two tiles in flight, operands staged through TMEM; 3 (default): three tiles, SS-mode layer-1 operands
 
 using namespace ptx;
 
@@ -78,7 +83,8 @@ __device__ __forceinline__ int slab_off(int n, int k16) {           // byte offs
 
 // =================================================================== weight packing (once per forward)
 // One image per direction (flow_out / flow_in); layers 1-2 and the classifier are shared.
-__global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ img_out, uint8_t* __restrict__ img_in) {
+__global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ img_out, uint8_t* __restrict__ img_in,
+                                    int cls_in_l3) {
   for (int dir = 0; dir < 2; ++dir) {
     uint8_t* img = dir == 0 ? img_out : img_in;
     const float* f0 = dir == 0 ? w.fout_w0 : w.fin_w0;
@@ -103,7 +109,11 @@ __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ im
     }
     for (int i = tid; i < FHP * 80; i += nt) {           // flow layer 0 (rows padded 56 -> 64)
       const int n = i / 80, k = i % 80;
-      put(OFF_L3H, OFF_L3L, L3_SLAB, n, k, n < FH ? f0[n * 80 + k] : 0.f);
+      // rows 56..63 are padding for the flow MLP; variant 3 puts the classifier's first layer there (it reads
+      // only the e' K step, columns 64..79)
+      float v = n < FH ? f0[n * 80 + k] : 0.f;
+      if (cls_in_l3 && n >= FH && k >= 64) v = w.cls_w0[(n - FH) * DE + (k - 64)];
+      put(OFF_L3H, OFF_L3L, L3_SLAB, n, k, v);
     }
     for (int i = tid; i < DN * FHP; i += nt) {           // flow layer 1 (K padded 56 -> 64)
       const int n = i / FHP, k = i % FHP;
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
 // x' for the next step's gathers and prow[r] = pinit[r] + W0[:, 32:64] x'.
 __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
                                                       int64_t num_nodes, int64_t num_out, int32_t chunks_out,
-                                                      const float* __restrict__ flow, const float* __restrict__ part,
+                                                      int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
                                                       const float* __restrict__ node_w, const float* __restrict__ node_b,
                                                       const float* __restrict__ w0, const float* __restrict__ pinit,
                                                       __half* __restrict__ xl_next, float* __restrict__ prow,
@@ -214,11 +224,11 @@ __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict_
       const int64_t s0 = ptr[r], s1 = ptr[r + 1];
       float v = 0.f;
       if (s1 > s0) {
-        const int64_t ca = (s0 - seg_base) / CHUNK, cb = (s1 - 1 - seg_base) / CHUNK;
+        const int64_t ca = (s0 - seg_base) >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
         if (ca == cb) {
           v = flow[r * 2 * DN + d * DN + lane];
         } else {
-          const bool first_in_chunk = (s0 - seg_base) % CHUNK == 0;
+          const bool first_in_chunk = ((s0 - seg_base) & ((1 << chunk_shift) - 1)) == 0;
           v = part[((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN + lane];
           for (int64_t t = ca + 1; t <= cb; ++t) v += part[((chunk_off + t) * 2) * DN + lane];
         }
@@ -501,8 +511,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
         // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
         const int64_t cs = t.base + wq * CHUNK;
         const int cw = t.cnt - wq * CHUNK;
-        if (lane == 0 && cw > 0 && cs > seg_base) t.nb = a.slot_row[cs - 1];
-        if (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end) t.nb = a.slot_row[cs + CHUNK];
+        // one predicated load (lane 0: the slot before the chunk, lane 31: the slot after it)
+        const bool want = (lane == 0 && cw > 0 && cs > seg_base) || (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end);
+        if (want) t.nb = a.slot_row[lane == 0 ? cs - 1 : cs + CHUNK];
       }
     }
     return t;
@@ -716,6 +727,439 @@ __global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
   if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
+// =================================================================== variant 3: three tiles in flight
+// Same arithmetic as mp_edge_tc_kernel, different resource plan:
+//  * the gathered x[col] rows are fetched by TMA (tile::gather4, 4 rows per instruction, 8 lanes per warp issue)
+//    straight into 128B-swizzled K-major shared-memory tiles and consumed by SS-mode MMAs (layers 1 and 3) - no
+//    per-thread loads, no register / TMEM staging of the widest operand;
+//  * the tile's own edge rows (e_init, e) go global -> registers -> TMEM by the half of the group that is idle
+//    during epilogue 2;
+//  * a tile needs 144 TMEM columns and 48 KB of shared memory, so THREE groups of 8 warps keep three tiles in
+//    flight per SM (24 warps); every edge row is served by two threads (halves A/B split the columns);
+//  * layer 1 of the next tile is issued as soon as layer 4 of the current one has retired, so epilogue 4 and the
+//    row sums run under it; row sums are split over all 8 warps (16 features each, 16-slot partial granule);
+//  * the classifier's first layer rides in the 8 padding columns of flow layer 0 (computed by the tensor core).
+constexpr int NG3 = 3, GT3 = 2 * TS, NTHREADS3 = NG3 * GT3;
+constexpr int CHUNK3 = 16, CHUNK3_SHIFT = 4;                                   // row-sum partial granule (slots)
+constexpr int T3_D1 = 0, T3_D2 = 80, T3_A3 = 96, T3_D3 = 0, T3_D4 = 80, T3_EH = 112, T3_EL = 128, T3_COLS = 144;
+constexpr int A_SLAB = TS * 32;                                                // one K=16 step of a 128-row A tile
+// group region: x_init[col] tile (128 rows x [hi 64 B | lo 64 B], SW128), x_lat[col] tile, message buffers
+constexpr int G3_XI = 0, G3_XL = 4 * A_SLAB, G3_MSG = 8 * A_SLAB, G3_BYTES = 12 * A_SLAB;
+constexpr int SM3_GRP = (IMG_BYTES + 1023) / 1024 * 1024;                      // swizzled tiles need 1 KB alignment
+constexpr int SM3_BAR = SM3_GRP + NG3 * G3_BYTES;                              // d_ready[3], xc_ready[3]
+constexpr int SM3_TMEM = SM3_BAR + 8 * 8;
+constexpr int SMEM3_BYTES = SM3_TMEM + 16;
+
+__global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_xi,
+                                                                    const __grid_constant__ CUtensorMap tm_xl) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  const int total_tiles = a.tiles_out + a.tiles_in;
+  int n_out_ctas = (int)(((int64_t)gridDim.x * a.tiles_out + total_tiles - 1) / total_tiles);
+  if (a.tiles_out > 0 && n_out_ctas == 0) n_out_ctas = 1;
+  if (a.tiles_in > 0 && n_out_ctas >= (int)gridDim.x) n_out_ctas = gridDim.x - 1;
+  if (a.tiles_in == 0) n_out_ctas = gridDim.x;
+  const bool dir_out = (int)blockIdx.x < n_out_ctas;
+  const int cta_in_dir = dir_out ? blockIdx.x : blockIdx.x - n_out_ctas;
+  const int ctas_in_dir = dir_out ? n_out_ctas : gridDim.x - n_out_ctas;
+  const int tiles_dir = dir_out ? a.tiles_out : a.tiles_in;
+  const int64_t seg_base = dir_out ? 0 : a.num_out;
+  const int64_t seg_end = dir_out ? a.num_out : a.num_edges;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM3_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM3_TMEM);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NG3; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[NG3 + i], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  const float* s_f = reinterpret_cast<const float*>(smem + OFF_F32);
+
+  const int g = warp >> 3;
+  const bool half_b = ((warp >> 2) & 1) != 0;
+  const int hb = half_b ? 1 : 0;
+  const int wq = warp & 3;
+  const int gt = wq * 32 + lane;                                       // edge row inside the tile = TMEM lane
+  const uint32_t tcol = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * T3_COLS;
+  const uint32_t tlane = tcol + ((uint32_t)(wq * 32) << 16);
+  uint8_t* grp = smem + SM3_GRP + g * G3_BYTES;
+  const uint32_t grp_addr = smem_u32(grp);
+  // this warp's private message buffer: 32 rows x 16 features (its half of the columns), bank-conflict-free
+  // both for the row-major writes (lane = row) and the feature-major reads of the row sums
+  float* s_msg = reinterpret_cast<float*>(grp + G3_MSG) + (wq * 2 + hb) * 32 * 16;
+  auto msg_at = [&](int row, int f) { return s_msg + ((row ^ ((row >> 4) & 1)) << 4) + ((f + (row >> 1)) & 15); };
+  uint64_t* d_ready = &bars[g];
+  uint64_t* xc_ready = &bars[NG3 + g];                                  // 4 gathering warps arrive + 32 KB of TMA bytes
+  uint32_t px = 0;
+  const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
+  const int dir_off = dir_out ? DN : 0;
+  const int bar_grp = 1 + g;
+  uint32_t pd = 0;
+  __half2 vmax = __floats2half2_rn(0.f, 0.f);
+
+  const uint64_t dzero = smem_desc_kmajor(0, 128, 256);
+  const uint64_t dsw = smem_desc_sw128(0);
+  const uint32_t img = smem_u32(smem);
+  auto ss3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+    const uint64_t adh = dsw + (uint64_t)(ah >> 4), adl = dsw + (uint64_t)(al >> 4);
+    const uint64_t bdh = dzero + (uint64_t)((img + off_h) >> 4), bdl = dzero + (uint64_t)((img + off_l) >> 4);
+    mma_ss(d, adh, bdh, idesc, first ? 0u : 1u);
+    mma_ss(d, adh, bdl, idesc, 1u);
+    mma_ss(d, adl, bdh, idesc, 1u);
+  };
+  auto ts3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+    const uint64_t bdh = dzero + (uint64_t)((img + off_h) >> 4), bdl = dzero + (uint64_t)((img + off_l) >> 4);
+    mma_ts(d, ah, bdh, idesc, first ? 0u : 1u);
+    mma_ts(d, ah, bdl, idesc, 1u);
+    mma_ts(d, al, bdh, idesc, 1u);
+  };
+  auto issue_layer = [&](int layer) {
+    if (layer == 1) { mbar_wait(xc_ready, px); px ^= 1; }               // the tile's x[col] rows have landed (TMA)
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t cb = tcol;
+      if (layer == 1) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {                               // K steps 0,1: x_init, 2,3: x_lat; hi at +0, lo at +64 B
+          const uint32_t at = grp_addr + (ks >> 1) * (G3_XL - G3_XI) + (ks & 1) * 32;
+          ss3(cb + T3_D1, at, at + 64, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB, idesc_f16(128, EH), ks == 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          ts3(cb + T3_D1, cb + T3_EH + 8 * ks, cb + T3_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB,
+              OFF_L1L + (4 + ks) * L1_SLAB, idesc_f16(128, EH), false);
+      } else if (layer == 2) {
+#pragma unroll
+        for (int ks = 0; ks < L2_KS; ++ks)
+          ts3(cb + T3_D2, cb + T3_D1 + 16 * ks, cb + T3_D1 + 16 * ks + 8, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
+              idesc_f16(128, DE), ks == 0);
+      } else if (layer == 3) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t at = grp_addr + (ks >> 1) * (G3_XL - G3_XI) + (ks & 1) * 32;
+          ss3(cb + T3_D3, at, at + 64, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB, idesc_f16(128, FHP), ks == 0);
+        }
+        ts3(cb + T3_D3, cb + T3_A3, cb + T3_A3 + 8, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, idesc_f16(128, FHP), false);
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < L4_KS; ++ks)
+          ts3(cb + T3_D4, cb + T3_D3 + 16 * ks, cb + T3_D3 + 16 * ks + 8, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
+              idesc_f16(128, DN), ks == 0);
+      }
+      mma_commit(d_ready);
+    }
+    __syncwarp();
+  };
+  auto publish_and_issue = [&](int layer) {
+    tc_wait_st();
+    tc_fence_before();
+    named_barrier(bar_grp, GT3);
+    if (!half_b && wq == 0) issue_layer(layer);
+  };
+  auto epilogue_chunk = [&](int col, const float* add) {
+    uint32_t acc[16];
+    tmem_ld16(tlane + col, acc);
+    tc_wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+      vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
+    }
+    tmem_st8(tlane + col, hi);
+    tmem_st8(tlane + col + 8, lo);
+  };
+
+  // x[col] rows of this quarter's 32 edges -> the group's swizzled operand tiles, 4 rows per TMA gather; half A
+  auto fetch_nodes = [&](int32_t c) {
+    const int l4 = (lane & 7) * 4;
+    const int32_t c0 = __shfl_sync(0xffffffffu, c, l4), c1 = __shfl_sync(0xffffffffu, c, l4 + 1);
+    const int32_t c2 = __shfl_sync(0xffffffffu, c, l4 + 2), c3 = __shfl_sync(0xffffffffu, c, l4 + 3);
+    if (lane == 0) mbar_arrive_expect_tx(xc_ready, 32 * 256);
+    __syncwarp();
+    if (lane < 8) {
+      const uint32_t dst = grp_addr + G3_XI + (wq * 32 + l4) * 128;
+      tma_gather4(dst, &tm_xi, xc_ready, c0, c1, c2, c3);
+      tma_gather4(dst + (G3_XL - G3_XI), &tm_xl, xc_ready, c0, c1, c2, c3);
+    }
+  };
+  // this thread's edge row [e_init | e] (split halves) -> TMEM operand columns; half B
+  struct EdgeRow { uint4 v[8]; };
+  auto load_edge_row = [&](int64_t base, int cnt) {
+    EdgeRow r;
+    const int64_t sl = base + (gt < cnt ? gt : cnt - 1);
+    const uint4* p0 = a.ei + sl * 4;
+    const uint4* p1 = a.es_in + sl * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { r.v[j] = __ldg(p0 + j); r.v[4 + j] = p1[j]; }
+    return r;
+  };
+  auto store_edge_row = [&](const EdgeRow& r) {
+    const uint32_t h0[8] = {r.v[0].x, r.v[0].y, r.v[0].z, r.v[0].w, r.v[1].x, r.v[1].y, r.v[1].z, r.v[1].w};
+    const uint32_t l0[8] = {r.v[2].x, r.v[2].y, r.v[2].z, r.v[2].w, r.v[3].x, r.v[3].y, r.v[3].z, r.v[3].w};
+    const uint32_t h1[8] = {r.v[4].x, r.v[4].y, r.v[4].z, r.v[4].w, r.v[5].x, r.v[5].y, r.v[5].z, r.v[5].w};
+    const uint32_t l1[8] = {r.v[6].x, r.v[6].y, r.v[6].z, r.v[6].w, r.v[7].x, r.v[7].y, r.v[7].z, r.v[7].w};
+    tmem_st8(tlane + T3_EH, h0);
+    tmem_st8(tlane + T3_EL, l0);
+    tmem_st8(tlane + T3_EH + 8, h1);
+    tmem_st8(tlane + T3_EL + 8, l1);
+  };
+
+  struct TileIdx { int64_t base; int cnt; int32_t r, x, nb; bool have; };   // x: col (half A) / slot_edge (half B)
+  auto load_idx = [&](int p) {
+    TileIdx t;
+    t.have = NG3 * p + g < tiles_dir;
+    t.base = 0; t.cnt = 0; t.r = 0; t.x = 0; t.nb = -1;
+    if (t.have) {
+      t.base = seg_base + (int64_t)(NG3 * p + g) * TS;
+      t.cnt = (int)(seg_end - t.base < TS ? seg_end - t.base : TS);
+      const int64_t slot = gt < t.cnt ? t.base + gt : t.base + t.cnt - 1;
+      t.r = a.slot_row[slot];
+      if (!half_b) t.x = a.slot_col[slot];
+      else if (a.logits != nullptr) t.x = a.slot_edge[slot];
+      const int64_t cs = t.base + wq * 32;
+      const int cw = t.cnt - wq * 32;
+      // one predicated load (lane 0: the slot before the quarter, lane 31: the slot after it)
+      const bool want = (lane == 0 && cw > 0 && cs > seg_base) || (lane == 31 && cw >= 32 && cs + 32 < seg_end);
+      if (want) t.nb = a.slot_row[lane == 0 ? cs - 1 : cs + 32];
+    }
+    return t;
+  };
+  // Row sums of this warp's 16 message features over its quarter's 32 slots, in slot order: lanes (sub, f) walk the
+  // two 16-slot granules.  A row's segment that lies inside one granule is written to `flow`; pieces that touch a
+  // granule edge go to the granule's two partial slots and are combined by the node kernel in fixed order.
+  auto row_sums = [&](const TileIdx& t) {
+    const int sub = lane >> 4, fl = lane & 15;
+    int cwq = t.cnt - wq * 32;
+    cwq = cwq < 0 ? 0 : (cwq > 32 ? 32 : cwq);
+    int cw = cwq - 16 * sub;
+    cw = cw < 0 ? 0 : (cw > 16 ? 16 : cw);
+    const int32_t nb_prev = __shfl_sync(0xffffffffu, t.nb, 0);
+    const int32_t nb_next = __shfl_sync(0xffffffffu, t.nb, 31);
+    const int32_t r15 = __shfl_sync(0xffffffffu, t.r, 15);
+    const int32_t r16 = __shfl_sync(0xffffffffu, t.r, 16);
+    const int32_t r_prev = sub ? r15 : nb_prev;
+    const int32_t r_next = sub ? nb_next : (cwq > 16 ? r16 : -1);
+    const int32_t r_after = __shfl_down_sync(0xffffffffu, t.r, 1);
+    const bool seg_end_here = fl < cw && (fl == cw - 1 || r_after != t.r);       // lane doubles as the row index here
+    const unsigned ends = (__ballot_sync(0xffffffffu, seg_end_here) >> (16 * sub)) & 0xffffu;
+    const int64_t chunk_id = chunk_off + ((t.base + wq * 32 - seg_base) >> CHUNK3_SHIFT) + sub;
+    const int f = 16 * hb + fl;
+    float sum = 0.f;
+    bool first_seg = true;
+#pragma unroll
+    for (int q = 0; q < CHUNK3; ++q) {
+      const int32_t rq = __shfl_sync(0xffffffffu, t.r, 16 * sub + q);
+      sum += *msg_at(16 * sub + q, fl);
+      if ((ends >> q) & 1u) {
+        const bool starts_before = first_seg && r_prev == rq;
+        const bool continues = q == cw - 1 && r_next == rq;
+        if (!starts_before && !continues) a.flow[(int64_t)rq * 2 * DN + dir_off + f] = sum;
+        else a.part[(chunk_id * 2 + (first_seg ? 0 : 1)) * DN + f] = sum;
+        sum = 0.f;
+        first_seg = false;
+      }
+    }
+    __syncwarp();
+  };
+  auto load_prow16 = [&](float* add, int32_t r, int ch) {
+    const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)r * EH + 16 * ch);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = __ldg(prp + j);
+      add[4 * j] = v.x; add[4 * j + 1] = v.y; add[4 * j + 2] = v.z; add[4 * j + 3] = v.w;
+    }
+  };
+
+  TileIdx cur = load_idx(cta_in_dir);
+  TileIdx nxt = load_idx(cta_in_dir + ctas_in_dir);
+  if (cur.have) {
+    if (!half_b) {
+      fetch_nodes(cur.x);
+    } else {
+      const EdgeRow er = load_edge_row(cur.base, cur.cnt);
+      store_edge_row(er);
+    }
+    publish_and_issue(1);
+  }
+  int p = cta_in_dir;
+  while (cur.have) {
+    const bool valid = gt < cur.cnt;
+    p += ctas_in_dir;
+    TileIdx nn = load_idx(p + ctas_in_dir);
+    if (nxt.have) {                                                   // next tile's hoisted row terms -> L1
+      const char* pr = reinterpret_cast<const char*>(a.prow + (int64_t)nxt.r * EH) + (half_b ? 192 : 0);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pr));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 127));
+    }
+    if (half_b && nn.have && (lane & 1) == 0) {                       // pull the edge rows two tiles ahead into L2
+      const int64_t sl = nn.base + (gt < nn.cnt ? gt : nn.cnt - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ei + sl * 4));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.es_in + sl * 4));
+    }
+
+    // ---- epilogue 1: + hoisted x[row] term (A: columns 0..47, B: 48..79)
+    {
+      const int ch0 = half_b ? 3 : 0;
+      float add[16];
+      load_prow16(add, cur.r, ch0);
+      mbar_wait(d_ready, pd); pd ^= 1;
+      tc_fence_after();
+      epilogue_chunk(T3_D1 + 16 * ch0, add);
+      load_prow16(add, cur.r, ch0 + 1);
+      epilogue_chunk(T3_D1 + 16 * (ch0 + 1), add);
+      if (!half_b) {
+        load_prow16(add, cur.r, 2);
+        epilogue_chunk(T3_D1 + 32, add);
+      }
+    }
+    publish_and_issue(2);
+
+    // ---- epilogue 2 (half A): e' -> state + layer-3 operand; half B stages the next tile's edge rows in TMEM
+    if (!half_b) {
+      mbar_wait(d_ready, pd); pd ^= 1;
+      tc_fence_after();
+      uint32_t acc[16];
+      tmem_ld16(tlane + T3_D2, acc);
+      float add[16];
+      ld_f32x16(add, s_f + F_B1);
+      tc_wait_ld();
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+        vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
+      }
+      tmem_st8(tlane + T3_A3, hi);
+      tmem_st8(tlane + T3_A3 + 8, lo);
+      publish_and_issue(3);
+      if (valid) {
+        uint4* dst = a.es_out + (cur.base + gt) * 4;
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    } else {
+      if (nxt.have) {                                                  // layer 1 (the only reader) has retired
+        const EdgeRow er = load_edge_row(nxt.base, nxt.cnt);
+        store_edge_row(er);
+      }
+      mbar_wait(d_ready, pd); pd ^= 1;
+      tc_fence_after();
+      publish_and_issue(3);
+    }
+    // ---- epilogue 3: g -> layer-4 operand (A: columns 0..31, B: 32..63; 56..63 carry the classifier's first layer)
+    mbar_wait(d_ready, pd); pd ^= 1;
+    tc_fence_after();
+    if (!half_b && nxt.have) fetch_nodes(nxt.x);                       // layer 3 was the last reader of x[col]
+    {
+      const int ch0 = half_b ? 2 : 0;
+      float add[16];
+      ld_f32x16(add, s_f + F_FB0 + 16 * ch0);
+      epilogue_chunk(T3_D3 + 16 * ch0, add);
+      ld_f32x16(add, s_f + F_FB0 + 16 * (ch0 + 1));                    // B: entries 8..15 are zero (padding)
+      if (!half_b) {
+        epilogue_chunk(T3_D3 + 16, add);
+      } else {
+        uint32_t acc[16];
+        tmem_ld16(tlane + T3_D3 + 48, acc);
+        float cb0[CH], cw1[CH];
+        ld_f32x8(cb0, s_f + F_CB0);
+        ld_f32x8(cw1, s_f + F_CW1);
+        tc_wait_ld();
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+          vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
+        }
+#pragma unroll
+        for (int j = 4; j < 8; ++j) { hi[j] = 0u; lo[j] = 0u; }        // K padding of layer 4
+        tmem_st8(tlane + T3_D3 + 48, hi);
+        tmem_st8(tlane + T3_D3 + 56, lo);
+        if (valid && a.logits != nullptr) {
+          float lg = s_f[F_CB1];
+#pragma unroll
+          for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(__uint_as_float(acc[8 + o]) + cb0[o], 0.f), cw1[o], lg);
+          a.logits[cur.x] = lg;
+        }
+      }
+    }
+    publish_and_issue(4);
+
+    // ---- layer 4 retired -> its operand columns are free: start the next tile's layer 1, then finish this tile
+    mbar_wait(d_ready, pd); pd ^= 1;
+    tc_fence_after();
+    if (nxt.have) publish_and_issue(1);
+    {
+      uint32_t acc[16];
+      tmem_ld16(tlane + T3_D4 + 16 * hb, acc);
+      float add[16];
+      ld_f32x16(add, s_f + F_FB1 + 16 * hb);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
+        *msg_at(lane, j) = valid ? m : 0.f;
+      }
+    }
+    __syncwarp();
+    row_sums(cur);
+    cur = nxt; nxt = nn;
+  }
+  {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&vmax);
+    if ((w & 0x7FFFu) >= 0x7BFFu || ((w >> 16) & 0x7FFFu) >= 0x7BFFu) atomicOr(a.status, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+// 2-D tensor map over split node rows [n][64 halfs] for the TMA row gather (box = one row, 128B swizzle)
+static int make_row_map(CUtensorMap* out, const void* base, int64_t n) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (encode == nullptr) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || fn == nullptr) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {64, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+
+int variant() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("MPN_TC_VARIANT");
+    v = (e != nullptr && e[0] == '2') ? 2 : 3;
+  }
+  return v;
+}
+
+
 long long* g_trace = nullptr;   // set by mpn_tc_set_trace (development only)
 
 struct TcWorkspace {
@@ -728,7 +1172,7 @@ struct TcWorkspace {
 
 static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   Carver cv(ws);
-  const int64_t chunks = ceil_div(e, CHUNK) + 8;
+  const int64_t chunks = ceil_div(e, CHUNK3) + 8;          // sized for the finer granule of the two kernel variants
   TcWorkspace w;
   w.xi = cv.take<__half>(n * 64);
   w.xl[0] = cv.take<__half>(n * 64);
@@ -778,10 +1222,11 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   static bool attr_set = false;
   if (!attr_set) {
     MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM3_BYTES));
     attr_set = true;
   }
   const int sms = sm_count();
-  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in); count_launch();
+  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, tc::variant() == 3 ? 1 : 0); count_launch();
   const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 4);
   tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, status);
   count_launch();
@@ -797,7 +1242,20 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   int grid = sms;
   if (grid > pairs) grid = pairs;
   if (tiles_out > 0 && tiles_in > 0 && grid < 2) grid = 2;
+  const int triples = (tiles_out + 2) / 3 + (tiles_in + 2) / 3;
+  int grid3 = sms;
+  if (grid3 > triples) grid3 = triples;
+  if (tiles_out > 0 && tiles_in > 0 && grid3 < 2) grid3 = 2;
 
+  CUtensorMap tm_xi, tm_xl[2];
+  if (tc::variant() == 3 && e > 0) {
+    if (tc::make_row_map(&tm_xi, m.xi, n) || tc::make_row_map(&tm_xl[0], m.xl[0], n) || tc::make_row_map(&tm_xl[1], m.xl[1], n)) {
+      set_error("mpn_mp_forward_tc: cuTensorMapEncodeTiled failed");
+      return MPN_ECUDA;
+    }
+  }
+  const int chunk_shift = tc::variant() == 3 ? tc::CHUNK3_SHIFT : 5;
+  const int64_t chunk = (int64_t)1 << chunk_shift;
   for (int step = 1; step <= num_steps; ++step) {
     const __half* xl_cur = m.xl[(step - 1) & 1];
     __half* xl_next = m.xl[step & 1];
@@ -805,7 +1263,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       tc::TcArgs a;
       a.slot_row = g->slot_row; a.slot_col = g->slot_col; a.slot_edge = g->slot_edge;
       a.num_edges = e; a.num_out = g->num_out; a.tiles_out = tiles_out; a.tiles_in = tiles_in;
-      a.chunks_out = ceil_div(g->num_out, tc::CHUNK);
+      a.chunks_out = ceil_div(g->num_out, chunk);
       a.xi = reinterpret_cast<const uint4*>(m.xi);
       a.xl = reinterpret_cast<const uint4*>(xl_cur);
       a.prow = m.prow;
@@ -818,12 +1276,14 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       a.status = status;
       a.trace = (step == 2) ? tc::g_trace : nullptr;
       if (profiling()) profile_mark(0, true, s);
-      tc::mp_edge_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, s>>>(a); count_launch();
+      if (tc::variant() == 3) tc::mp_edge_tc3_kernel<<<grid3, tc::NTHREADS3, tc::SMEM3_BYTES, s>>>(a, tm_xi, tm_xl[(step - 1) & 1]);
+      else tc::mp_edge_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, s>>>(a);
+      count_launch();
       if (profiling()) profile_mark(0, false, s);
     }
     if (profiling()) profile_mark(1, true, s);
     tc::node_tc_kernel<<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
-                                             (int32_t)ceil_div(g->num_out, tc::CHUNK), m.flow, m.part, w->node_w,
+                                             (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
                                              w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
                                              step == num_steps ? x_out : nullptr, status);
     count_launch();

@@ -31,10 +31,11 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return d;
 }
 
-template <int N, int K>
+template <int N, int K, bool SS>
 __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
                                                     float* __restrict__ D) {
   __shared__ __align__(128) __half sB[N * K];            // per k-step slab: [n/8][khalf][8][8]
+  __shared__ __align__(128) __half sA[SS ? 128 * K : 8];  // SS mode: A in the same canonical layout
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -44,6 +45,13 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ A
     const int ks = k / 16, kk = k % 16;
     const int off = ks * N * 16 + (n / 8) * 128 + (kk / 8) * 64 + (n % 8) * 8 + (kk % 8);
     sB[off] = B[idx];
+  }
+  if (SS) {
+    for (int idx = tid; idx < 128 * K; idx += 128) {
+      const int m = idx / K, k = idx % K;
+      const int ks = k / 16, kk = k % 16;
+      sA[ks * 128 * 16 + (m / 8) * 128 + (kk / 8) * 64 + (m % 8) * 8 + (kk % 8)] = A[idx];
+    }
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -80,10 +88,18 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ A
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t bdesc = make_b_desc(smem_u32(sB) + ks * N * 32, 128, 256);
       const uint32_t acc = ks > 0 ? 1u : 0u;
+      if (SS) {
+        const uint64_t adesc = make_b_desc(smem_u32(sA) + ks * 128 * 32, 128, 256);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tbase + d_col),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+      } else {
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
           "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tbase + d_col),
           "r"(tbase + ks * 8), "l"(bdesc), "r"(idesc), "r"(acc));
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)));
   }
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ A
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tbase));
 }
 
-template <int N, int K>
+template <int N, int K, bool SS>
 int run() {
   std::vector<__half> hA(128 * K), hB(N * K);
   std::vector<float> fA(128 * K), fB(N * K), ref(128 * N), out(128 * N);
@@ -130,12 +146,12 @@ int run() {
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xff, out.size() * 4));
-  probe_kernel<N, K><<<1, 128>>>(dA, dB, dD);
+  probe_kernel<N, K, SS><<<1, 128>>>(dA, dB, dD);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0; int bad = 0;
   for (size_t i = 0; i < out.size(); ++i) { double e = fabs(out[i] - ref[i]); if (e > maxerr) maxerr = e; if (!(e <= 1e-3)) ++bad; }
-  printf("N=%d K=%d: max err %.3e, bad %d / %zu  (out[0]=%f ref[0]=%f out[last]=%f ref[last]=%f)\n", N, K, maxerr, bad,
+  printf("%s N=%d K=%d: max err %.3e, bad %d / %zu  (out[0]=%f ref[0]=%f out[last]=%f ref[last]=%f)\n", SS ? "SS" : "TS", N, K, maxerr, bad,
          out.size(), out[0], ref[0], out.back(), ref.back());
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
   return bad;
@@ -143,11 +159,11 @@ int run() {
 
 int main() {
   int bad = 0;
-  bad += run<16, 16>();
-  bad += run<16, 80>();
-  bad += run<80, 96>();
-  bad += run<64, 80>();
-  bad += run<32, 64>();
+  bad += run<16, 16, false>();
+  bad += run<80, 96, false>();
+  bad += run<16, 16, true>();
+  bad += run<80, 96, true>();
+  bad += run<64, 64, true>();
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad != 0;
 }
