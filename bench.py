@@ -335,7 +335,9 @@ def run_b200(a):
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_mp_edge_tc_traffic.json')))
             if os.environ.get('MPN_ENGINE', 'auto') != 'fp32':
-                traffic = tr['dram_bytes_per_edge_update'] * edges      # ncu dram read+write per edge-update x this launch's edges
+                per_edge = tr['dram_bytes_per_edge_update'] if os.environ.get('MPN_TC_VARIANT', '3') != '2' \
+                    else tr['previous_kernel']['dram_bytes_per_edge_update']
+                traffic = per_edge * edges      # ncu dram read+write per edge-update x this launch's edges
         except (OSError, KeyError, ValueError):
             pass
         line = dict(
@@ -351,7 +353,7 @@ def run_b200(a):
                      h2d_bytes_per_step=int(h2d_total), d2h_bytes_per_step=int(d2h_total),
                      graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3)),
             gpu_launches=int(launches),
-            roofline=dict(bound='hbm', kernel='mp_edge_tc_kernel' if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
+            roofline=dict(bound='hbm', kernel=('mp_edge_tc3_kernel' if os.environ.get('MPN_TC_VARIANT', '3') != '2' else 'mp_edge_tc_kernel') if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
                           frac=achieved / peak if peak else None, traffic=traffic, algorithmic_bytes=bytes_per_launch,
                           peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                           avg_launch_ms=avg_ms, launches=edge_launches,

@@ -24,9 +24,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   while (!done) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(a), "r"(parity)
+        : "r"(a), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware instead of re-polling
         : "memory");
   }
 }
