@@ -25,7 +25,13 @@ class Graph(object):
 
     @property
     def num_nodes(self):
+        if getattr(self, '_num_nodes', None) is not None:        # pinned by to_lightweight_graph before x is dropped
+            return self._num_nodes
         return self.x.size(0)
+
+    @num_nodes.setter
+    def num_nodes(self, n):
+        self._num_nodes = int(n)
 
     @property
     def num_edges(self):

@@ -65,3 +65,51 @@ def compute_edge_feats_dict(edge_ixs, det_df, fps, use_cuda):
     names = ('secs_time_dists', 'norm_feet_x_dists', 'norm_feet_y_dists', 'bb_height_dists', 'bb_width_dists')
     out = {n: attr[:p, i].contiguous() for i, n in enumerate(names)}
     return out if use_cuda else {k: v.cpu() for k, v in out.items()}
+
+
+def to_undirected_graph(mot_graph, attrs_to_update=('edge_preds', 'edge_labels')):
+    """Keep one (i < j) copy of every directed edge pair of ``mot_graph.graph_obj`` (sorted by (i, j)) and
+    average the attributes in ``attrs_to_update`` over the two copies.  Runs on the device the graph
+    lives on.  reference: utils/graph.py:165-185"""
+    go = mot_graph.graph_obj
+    ei = go.edge_index
+    e = ei.shape[1]
+    half = e // 2
+    # fast path: the layout every graph built here has -- [pairs with i < j sorted by (i, j) | the same pairs flipped]
+    structured = e % 2 == 0 and e > 0 and bool(
+        (ei[0, :half] < ei[1, :half]).all() and torch.equal(ei[:, half:], ei[:, :half].flip(0)))
+    if structured:
+        n = int(ei.max()) + 1
+        key = ei[0, :half] * n + ei[1, :half]
+        structured = bool((key[1:] > key[:-1]).all())
+    if structured:
+        go.edge_index = ei[:, :half].contiguous()
+        for name in attrs_to_update:
+            if hasattr(go, name):
+                a = getattr(go, name)
+                setattr(go, name, (a[:half] + a[half:]) / 2)
+        return
+    sorted_edges, _ = torch.sort(ei, dim=0)
+    undirected, inverse = torch.unique(sorted_edges, return_inverse=True, dim=1)
+    assert sorted_edges.shape[1] == 2 * undirected.shape[1], "Some edges were not duplicated"
+    go.edge_index = undirected
+    for name in attrs_to_update:
+        if hasattr(go, name):
+            a = getattr(go, name)
+            s = torch.zeros(undirected.shape[1], dtype=a.dtype, device=a.device).index_add_(0, inverse, a)
+            c = torch.zeros_like(s).index_add_(0, inverse, torch.ones_like(a))
+            setattr(go, name, s / c.clamp(min=1))                       # scatter_mean
+
+
+def to_lightweight_graph(mot_graph, attrs_to_del=('reid_emb_dists', 'x', 'edge_attr', 'edge_labels')):
+    """Delete what inference no longer needs and prune edges predicted below 0.5.
+    reference: utils/graph.py:187-207"""
+    go = mot_graph.graph_obj
+    go.num_nodes = go.num_nodes                                         # pin the count: ``x`` is deleted below (:194)
+    go.node_names = torch.arange(go.num_nodes, device=go.edge_index.device)
+    for name in attrs_to_del:
+        if hasattr(go, name):
+            delattr(go, name)
+    keep = go.edge_preds >= 0.5
+    go.edge_index = go.edge_index.T[keep].T
+    go.edge_preds = go.edge_preds[keep]

@@ -30,7 +30,7 @@ import pandas as pd  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 from mot_neural_solver.models.mpn import MOTMPNet as RefMOTMPNet  # noqa: E402
 from mot_neural_solver.utils.graph import (  # noqa: E402
-    compute_edge_feats_dict, get_knn_mask, get_time_valid_conn_ixs)
+    compute_edge_feats_dict, get_knn_mask, get_time_valid_conn_ixs, to_lightweight_graph, to_undirected_graph)
 
 from mpntrackseg_b200 import synth  # noqa: E402
 from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params  # noqa: E402
@@ -192,6 +192,82 @@ def run_tracker_case():
         param_checksum=checksum(*P.values()))
 
 
+class _GraphObj:
+    """The attribute bag the reference's to_undirected_graph / to_lightweight_graph work on."""
+
+    def device(self):
+        return torch.device('cpu')
+
+
+class _MotGraph:
+    pass
+
+
+def run_tracker_sequence_case():
+    """All sliding windows of the TRACKER_CASE sequence, averaged per edge, then merged to an undirected
+    graph and pruned at 0.5 -- the loop of MPNTracker._evaluate_graph_in_batches
+    (reference: tracker/mpn_tracker.py:153-207) inlined around the imported reference functions, with the
+    weights of the tracker_window fixture.  Stored for both settings of set_pruned_edges_to_inactive."""
+    c = TRACKER_CASE
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    mp = default_graph_model_params(*c['steps'])
+    fpg = ds['frames_per_graph']
+    n_cand, edge_index, edge_attr, dists = ref_build_graph(win, ds, True, 1 * (fpg - 1))
+    gold_w = dict(np.load(os.path.join(HERE, 'tracker_window.npz')))
+    P = synth.make_params(mp, seed=c['wseed'], gain=c['gain'])
+    key = [k for k in P if k.startswith('classifier.edge_model') and k.endswith('bias')][-1]
+    P[key] = P[key] - float(gold_w['bias_shift'])
+    assert checksum(*P.values()) == str(gold_w['param_checksum'])
+    model = RefMOTMPNet(mp).eval()
+    model.load_state_dict(P, strict=True)
+    all_frames = np.array(sorted(set(win.frame.tolist())))
+    frame_num_per_node = win.frame
+    node_names = torch.arange(win.N)
+    out = {}
+    for inactive in (False, True):
+        overall = torch.zeros(edge_index.shape[1])
+        num = overall.clone()
+        for start_frame, end_frame in zip(all_frames, all_frames[fpg - 1:]):                  # :167
+            nodes_mask = (start_frame <= frame_num_per_node) & (frame_num_per_node <= end_frame)
+            edges_mask = nodes_mask[edge_index[0]] & nodes_mask[edge_index[1]]
+            sub_ei = edge_index.T[edges_mask].T - node_names[nodes_mask][0]
+            sub_attr, sub_d = edge_attr[edges_mask], dists[edges_mask]
+            knn_mask = get_knn_mask(pwise_dist=sub_d, edge_ixs=sub_ei, num_nodes=int(nodes_mask.sum()),
+                                    top_k_nns=ds['top_k_nns'], use_cuda=False,
+                                    reciprocal_k_nns=ds['reciprocal_k_nns'], symmetric_edges=True)   # :107-110
+            data = Data()
+            data.x, data.x_ext = win.x[nodes_mask], None
+            data.edge_index, data.edge_attr = sub_ei.T[knn_mask].T, sub_attr[knn_mask]
+            with torch.no_grad():
+                core = core_forward(model, data)
+            pruned = torch.sigmoid(core['classified_edges'][-1].view(-1))                     # :129
+            edge_preds = torch.zeros(knn_mask.shape[0])
+            edge_preds[knn_mask] = pruned                                                     # :133-134
+            pred_mask = torch.ones_like(knn_mask) if inactive else knn_mask                   # :137-141
+            overall[edges_mask] += edge_preds                                                 # :195
+            num[torch.where(edges_mask)[0][pred_mask]] += 1                                   # :197
+        final = overall / num                                                                 # :203
+        final[torch.isnan(final)] = 0
+        g = _MotGraph()
+        g.graph_obj = _GraphObj()
+        g.graph_obj.edge_index, g.graph_obj.edge_preds, g.graph_obj.num_nodes = edge_index.clone(), final.clone(), win.N
+        to_undirected_graph(g, attrs_to_update=('edge_preds', 'edge_labels'))                 # :206
+        und_ei, und_p = g.graph_obj.edge_index.clone(), g.graph_obj.edge_preds.clone()
+        to_lightweight_graph(g)                                                               # :207
+        tag = 'inactive' if inactive else 'knn'
+        out[f'directed_preds_{tag}'] = final.numpy()
+        out[f'undirected_edge_index_{tag}'] = und_ei.numpy().astype(np.int32)
+        out[f'undirected_preds_{tag}'] = und_p.numpy()
+        out[f'light_edge_index_{tag}'] = g.graph_obj.edge_index.numpy().astype(np.int32)
+        out[f'light_preds_{tag}'] = g.graph_obj.edge_preds.numpy()
+        print('tracker_sequence', tag, dict(windows=len(all_frames) - fpg + 1, E_full=edge_index.shape[1],
+                                            undirected=und_ei.shape[1], kept=int(g.graph_obj.edge_index.shape[1]),
+                                            never_predicted=int((num == 0).sum())))
+    np.savez_compressed(os.path.join(HERE, 'tracker_sequence.npz'), **out,
+                        input_checksum=gold_w['input_checksum'], param_checksum=gold_w['param_checksum'])
+
+
 if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count() or 1)
     only = sys.argv[1:]
@@ -200,3 +276,5 @@ if __name__ == '__main__':
             run_case(name, case)
     if not only or 'tracker_window' in only:
         run_tracker_case()
+    if not only or 'tracker_sequence' in only:
+        run_tracker_sequence_case()

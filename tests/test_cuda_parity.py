@@ -160,6 +160,90 @@ def test_tracker_window_prune_and_predict():
     assert float((preds.cpu() - torch.from_numpy(gold['edge_preds'])).abs().max()) <= PROB_TOL
 
 
+class _FullGraph(object):
+    pass
+
+
+def _sequence_full_graph(c):
+    from mpntrackseg_b200.data.mot_graph import MOTGraph
+    win, ds = c['win'], c['ds']
+    mg = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
+                  max_frame_dist=ds['frames_per_graph'] - 1)
+    mg.construct_graph_object()
+    full = _FullGraph()
+    full.graph_obj, full.graph_df = mg.graph_obj, synth.det_columns(win)
+    full.frames = sorted(set(win.frame.tolist()))
+    full.frames_per_graph = ds['frames_per_graph']
+    return full
+
+
+@pytest.mark.parametrize('inactive', [False, True])
+@pytest.mark.parametrize('schedule', ['batched', 'window_by_window'])
+def test_tracker_sequence_sliding_windows(inactive, schedule):
+    """MPNTracker._evaluate_graph_in_batches (mpn_tracker.py:143-210) -- batched B200 schedule and the
+    reference's window-by-window schedule -- against the reference's golden sequence output."""
+    import os
+    from mpntrackseg_b200.tracker import MPNTracker
+    c = load_case('tracker_window')
+    seq = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'tracker_sequence.npz')))
+    tag = 'inactive' if inactive else 'knn'
+    tracker = MPNTracker(dataset=None, graph_model=make_model(c['mp'], c['P']), use_gt=False,
+                         eval_params={'set_pruned_edges_to_inactive': inactive}, dataset_params=c['ds'], window_batch=2)
+    tracker.full_graph = _sequence_full_graph(c)
+    go = tracker.full_graph.graph_obj
+    if schedule == 'batched':
+        assert tracker._structured(go)
+        tracker._evaluate_batched()
+    else:
+        tracker._evaluate_window_by_window(None)
+    directed = go.edge_preds.cpu().numpy()
+    assert np.abs(directed - seq[f'directed_preds_{tag}']).max() <= PROB_TOL
+    from mpntrackseg_b200.utils.graph import to_lightweight_graph, to_undirected_graph
+    to_undirected_graph(tracker.full_graph, attrs_to_update=('edge_preds', 'edge_labels'))
+    assert np.array_equal(go.edge_index.cpu().numpy(), seq[f'undirected_edge_index_{tag}'].astype(np.int64))
+    und = go.edge_preds.cpu().numpy()
+    assert np.abs(und - seq[f'undirected_preds_{tag}']).max() <= PROB_TOL
+    to_lightweight_graph(tracker.full_graph)
+    assert not hasattr(go, 'x') and go.num_nodes == c['win'].N
+    # identical decisions outside +-1e-3 of the 0.5 threshold
+    ref_p = seq[f'undirected_preds_{tag}']
+    sure = np.abs(ref_p - 0.5) > PROB_TOL
+    kept = np.zeros(ref_p.shape[0], dtype=bool)
+    und_ei = seq[f'undirected_edge_index_{tag}'].astype(np.int64)
+    n = c['win'].N
+    pos = {int(a) * n + int(b): i for i, (a, b) in enumerate(und_ei.T)}
+    for a, b in go.edge_index.cpu().numpy().T:
+        kept[pos[int(a) * n + int(b)]] = True
+    assert np.array_equal(kept[sure], (ref_p >= 0.5)[sure])
+
+
+def test_tracker_full_entry_point_and_general_undirected_merge():
+    """_evaluate_graph_in_batches end to end, and to_undirected_graph on a shuffled (unstructured) edge list."""
+    import os
+    from mpntrackseg_b200.data.mot_graph import Graph
+    from mpntrackseg_b200.tracker import MPNTracker
+    from mpntrackseg_b200.utils.graph import to_undirected_graph
+    c = load_case('tracker_window')
+    seq = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'tracker_sequence.npz')))
+    tracker = MPNTracker(graph_model=make_model(c['mp'], c['P']), eval_params={'set_pruned_edges_to_inactive': False},
+                         dataset_params=c['ds'])
+    tracker.full_graph = _sequence_full_graph(c)
+    tracker._evaluate_graph_in_batches()
+    go = tracker.full_graph.graph_obj
+    assert go.edge_index.shape[1] == go.edge_preds.shape[0] and bool((go.edge_preds >= 0.5).all())
+    assert abs(go.edge_index.shape[1] - seq['light_edge_index_knn'].shape[1]) <= 2
+    # general path: shuffled directed edges
+    ei = torch.from_numpy(np.concatenate((seq['undirected_edge_index_knn'], seq['undirected_edge_index_knn'][::-1]), axis=1)
+                          .astype(np.int64))
+    p = torch.from_numpy(seq['directed_preds_knn'])
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(3))
+    full = _FullGraph()
+    full.graph_obj = Graph(x=torch.zeros(c['win'].N, 1), edge_index=ei[:, perm].to(dev()), edge_preds=p[perm].to(dev()))
+    to_undirected_graph(full)
+    assert np.array_equal(full.graph_obj.edge_index.cpu().numpy(), seq['undirected_edge_index_knn'].astype(np.int64))
+    np.testing.assert_allclose(full.graph_obj.edge_preds.cpu().numpy(), seq['undirected_preds_knn'], rtol=1e-6, atol=1e-7)
+
+
 # ------------------------------------------------------------------ layout
 def test_edge_layout_invariants():
     from mpntrackseg_b200 import ops

@@ -1,5 +1,7 @@
 """Pins the CPU oracle (oracle/) against outputs of the unmodified reference
 (tests/golden/*.npz, written by tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -79,6 +81,32 @@ def test_tracker_window_glue():
         out = mpn_ref.mpn_forward(c['P'], c['mp'], win.x[nodes], ei, ea)
     preds = mpn_ref.window_edge_preds(out['classified_edges'], keep)
     np.testing.assert_allclose(preds.numpy(), gold['edge_preds'], rtol=1e-5, atol=1e-6)
+
+
+def test_tracker_sequence_sliding_windows():
+    """mpn_tracker.py:153-207 restatement (all windows, per-edge averaging, undirected merge, pruning at 0.5)
+    against the loop run around the imported reference functions (fixture tracker_sequence.npz)."""
+    from oracle import tracker_ref
+    c = load_case('tracker_window')
+    seq = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'tracker_sequence.npz')))
+    assert str(seq['param_checksum']) == str(c['gold']['param_checksum'])
+    win, ds = c['win'], c['ds']
+    fpg = ds['frames_per_graph']
+    g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds,
+                              inference_mode=True, max_frame_dist=fpg - 1)
+    for tag, inactive in (('knn', False), ('inactive', True)):
+        with torch.no_grad():
+            final = tracker_ref.evaluate_graph_in_batches(
+                c['P'], c['mp'], ds, {'set_pruned_edges_to_inactive': inactive}, win.frame, win.x, g['edge_index'],
+                g['edge_attr'], g['reid_emb_dists'], fpg)
+        np.testing.assert_allclose(final.numpy(), seq[f'directed_preds_{tag}'], rtol=1e-5, atol=1e-6)
+        und_ei, (und_p,) = tracker_ref.to_undirected(g['edge_index'], [final])
+        assert np.array_equal(und_ei.numpy(), seq[f'undirected_edge_index_{tag}'].astype(np.int64))
+        np.testing.assert_allclose(und_p.numpy(), seq[f'undirected_preds_{tag}'], rtol=1e-5, atol=1e-6)
+        # pruning at 0.5 from the fixture's own averaged predictions (no threshold noise)
+        li, lp = tracker_ref.to_lightweight(und_ei, torch.from_numpy(seq[f'undirected_preds_{tag}']))
+        assert np.array_equal(li.numpy(), seq[f'light_edge_index_{tag}'].astype(np.int64))
+        assert np.array_equal(lp.numpy(), seq[f'light_preds_{tag}'])
 
 
 def test_knn_mask_independent_restatement():
