@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
                                                             int32_t* __restrict__ thr_idx) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
-  __shared__ int s_remaining;
+  __shared__ int s_remaining, s_count;
+  __shared__ int32_t s_found;
   const int64_t i = blockIdx.x;
   if (row_mask != nullptr && row_mask[i] == 0) return;
   int64_t lo = 0, hi = num_graphs;                                  // window of node i
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
     if (threadIdx.x == 0) { thr_key[i] = 0xffffffffu; thr_idx[i] = (int32_t)n; }
     return;
   }
-  if (threadIdx.x == 0) { s_prefix = 0u; s_remaining = (int)k; }
+  if (threadIdx.x == 0) { s_prefix = 0u; s_remaining = (int)k; s_found = (int32_t)(n - 1); }
   uint32_t mask = 0u;
+  const int lane = threadIdx.x & 31;
   for (int shift = 24; shift >= 0; shift -= 8) {
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -121,19 +123,43 @@ __global__ void __launch_bounds__(256) batch_row_kth_kernel(const float* __restr
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int rem = s_remaining, b = 0;
-      for (; b < 256; ++b) { if (hist[b] >= rem) break; rem -= hist[b]; }
-      s_remaining = rem;
-      s_prefix = prefix | ((uint32_t)b << shift);
+    if (threadIdx.x < 32) {
+      // bin holding the `remaining`-th element: lane l owns bins 8l..8l+7, warp scan over the lane totals
+      int h[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h[q] = hist[8 * lane + q]; tot += h[q]; }
+      int incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += v; }
+      const int rem0 = s_remaining;
+      const bool here = incl >= rem0 && incl - tot < rem0;              // exactly one lane
+      if (here) {
+        int rem = rem0 - (incl - tot), b = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (h[q] >= rem) { b = q; break; } rem -= h[q]; }
+        s_remaining = rem;
+        s_prefix = prefix | ((uint32_t)(8 * lane + b) << shift);
+        s_count = h[b];
+      }
     }
     mask |= 255u << shift;
     __syncthreads();
   }
-  if (threadIdx.x < 32) {                                           // ties: first `need` of them in index order
-    const uint32_t tau = s_prefix;
-    const int need = s_remaining;
-    const int lane = threadIdx.x;
+  const uint32_t tau = s_prefix;
+  const int need = s_remaining;
+  if (s_count == need) {
+    // no tie straddles the boundary: the k-th element (ties by ascending index) is the LAST element equal to tau
+    if (threadIdx.x == 0) s_found = -1;
+    __syncthreads();
+    int32_t mine = -1;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
+      if (order_key_f(rowp[j]) == tau) mine = (int32_t)j;                // ascending j per thread
+    if (mine >= 0) atomicMax(&s_found, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) { thr_key[i] = tau; thr_idx[i] = s_found; }
+    return;
+  }
+  if (threadIdx.x < 32) {                                           // a tie straddles the boundary: first `need` in index order
     int seen = 0;
     int32_t found = (int32_t)(n - 1);
     for (int64_t j0 = 0; j0 < n; j0 += 32) {

@@ -5,7 +5,9 @@
 // the exact fp32 formula of the reference (same kernel arithmetic as knn_graph.cu) and re-ranked, and the
 // distances attached to the kept pairs are always recomputed exactly.  The kept edge set is therefore the
 // one the exact path produces.
+#include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -32,7 +34,8 @@ __device__ __forceinline__ int slab_off(int n, int k16) {
 // warp per node: packed fp16 hi/lo image of its row inside its 128-row tile, ||a||^2 and sum(a).
 __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, const int64_t* __restrict__ gptr,
                                  int64_t num_graphs, const int64_t* __restrict__ tile_off, int64_t num_nodes,
-                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1) {
+                                 uint8_t* __restrict__ img, float* __restrict__ norm2, float* __restrict__ sum1,
+                                 int32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -44,8 +47,10 @@ __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, co
     const int64_t tile = tile_off[lo] + li / TS;
     const int n = (int)(li % TS);
     float s2 = 0.f, s1 = 0.f;
+    bool ovf = false;
     for (int64_t k = lane; k < dim; k += 32) {
       const float v = reid[i * dim + k];
+      ovf |= !(fabsf(v) < 65000.f);                              // outside the fp16 range: the caller reruns exactly
       s2 = fmaf(v, v, s2);
       s1 += v;
       const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
@@ -55,6 +60,7 @@ __global__ void pack_reid_kernel(const float* __restrict__ reid, int64_t dim, co
     }
     for (int d = 16; d > 0; d >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); }
     if (lane == 0) { norm2[i] = s2; sum1[i] = s1; }
+    if (ovf) atomicOr(status, 1);
   }
 }
 
@@ -283,19 +289,179 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const float* __restrict
   }
 }
 
-__global__ void tile_offsets_kernel(const int64_t* __restrict__ gptr, int64_t num_graphs, int64_t* __restrict__ tile_off) {
+__global__ void tile_offsets_kernel(const int64_t* __restrict__ gptr, int64_t num_graphs, int64_t* __restrict__ tile_off,
+                                    int64_t* __restrict__ tri_off) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int64_t acc = 0;
-    for (int64_t g = 0; g < num_graphs; ++g) { tile_off[g] = acc; acc += (gptr[g + 1] - gptr[g] + TS - 1) / TS; }
+    int64_t acc = 0, tri = 0;
+    for (int64_t g = 0; g < num_graphs; ++g) {
+      const int64_t nt = (gptr[g + 1] - gptr[g] + TS - 1) / TS;
+      tile_off[g] = acc; acc += nt;
+      tri_off[g] = tri; tri += nt * nt;                         // the TMA kernel walks ALL nt x nt tiles of a window
+    }
     tile_off[num_graphs] = acc;
+    tri_off[num_graphs] = tri;
   }
+}
+
+// ------------------------------------------------------------------ TMA-fed, warp-specialised Gram kernel
+// Persistent CTA per SM over the flattened list of ALL 128x128 tiles of all windows (both triangles: every element
+// is stored transposed, D[col][row], so that a warp's 32 rows write 32 consecutive floats -- storing the direct
+// element as well would be a 32-sector scatter per instruction and was the bottleneck).  The packed
+// fp16 hi/lo image of a 128-row tile serves as BOTH operands (the Gram matrix is symmetric), so nothing is split
+// or staged by threads: warp 16 streams 32 KB operand chunks with TMA bulk copies into a 3-stage ring, warp 17
+// issues the SS-mode MMAs (3 per K step) into one of two TMEM accumulators, warps 0-15 turn the previous
+// accumulator into distances (each warp: its TMEM lane quarter x a 32-column group) and store them.
+constexpr int G2_STAGES = 3, G2_EPI_WARPS = 16, G2_THREADS = 32 * (G2_EPI_WARPS + 2);
+constexpr int G2_SM_BAR = G2_STAGES * 2 * CHUNK_BYTES;      // full[3], empty[3], acc_full[2], acc_empty[2]
+constexpr int G2_SM_TMEM = G2_SM_BAR + 10 * 8;
+constexpr int G2_SMEM_BYTES = G2_SM_TMEM + 16;
+
+struct Gram2Args {
+  const int64_t* frame; const int64_t* gptr; const int64_t* doff; const int64_t* tile_off; const int64_t* tri_off;
+  const uint8_t* img; const float* norm2; const float* sum1;
+  int64_t num_graphs, max_dist, dim; float* dense;
+};
+
+struct TileCursor {                                          // flattened tile id -> (window, ti, tj); ids only grow
+  int64_t w = 0;
+  __device__ __forceinline__ void seek(const Gram2Args& a, int64_t t, int& ti, int& tj, int& nt) {
+    while (t >= a.tri_off[w + 1]) ++w;
+    const int rem = (int)(t - a.tri_off[w]);
+    nt = (int)(a.tile_off[w + 1] - a.tile_off[w]);
+    ti = rem / nt;
+    tj = rem - ti * nt;
+  }
+};
+
+__global__ void __launch_bounds__(G2_THREADS, 1) gram_blocks2_kernel(Gram2Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_SM_BAR);
+  uint64_t* empty = full + G2_STAGES;
+  uint64_t* acc_full = empty + G2_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G2_SM_TMEM);
+  if (tid == 0) {
+    for (int i = 0; i < G2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], G2_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tcol = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int nchunks = (int)(a.dim / KC);
+  const int64_t total = a.tri_off[a.num_graphs];
+  TileCursor cur;
+
+  if (warp == G2_EPI_WARPS) {
+    // ---- TMA producer
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+      int ti, tj, nt;
+      cur.seek(a, t, ti, tj, nt);
+      const uint8_t* abase = a.img + (a.tile_off[cur.w] + ti) * (int64_t)nchunks * CHUNK_BYTES;
+      const uint8_t* bbase = a.img + (a.tile_off[cur.w] + tj) * (int64_t)nchunks * CHUNK_BYTES;
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const uint32_t s = it % G2_STAGES, ph = (it / G2_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);                          // the MMAs that read this stage have retired
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(smem + s * 2 * CHUNK_BYTES);
+          mbar_arrive_expect_tx(&full[s], 2 * CHUNK_BYTES);
+          tma_bulk_g2s(dst, abase + (int64_t)c * CHUNK_BYTES, CHUNK_BYTES, &full[s]);
+          tma_bulk_g2s(dst + CHUNK_BYTES, bbase + (int64_t)c * CHUNK_BYTES, CHUNK_BYTES, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == G2_EPI_WARPS + 1) {
+    // ---- MMA issuer
+    const uint64_t dbase = smem_desc_kmajor(0, 128, 256);
+    uint32_t it = 0, tl = 0;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);                     // the epilogue has drained this accumulator
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const uint32_t s = it % G2_STAGES, ph = (it / G2_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t ab = smem_u32(smem + s * 2 * CHUNK_BYTES), bb = ab + CHUNK_BYTES;
+          const uint32_t d = tcol + buf * TS;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t ah = dbase + (uint64_t)((ab + ks * SLAB) >> 4), al = dbase + (uint64_t)((ab + (KC / 16 + ks) * SLAB) >> 4);
+            const uint64_t bh = dbase + (uint64_t)((bb + ks * SLAB) >> 4), bl = dbase + (uint64_t)((bb + (KC / 16 + ks) * SLAB) >> 4);
+            mma_ss(d, ah, bh, idesc_f16(128, TS), (c > 0 || ks > 0) ? 1u : 0u);
+            mma_ss(d, ah, bl, idesc_f16(128, TS), 1u);
+            mma_ss(d, al, bh, idesc_f16(128, TS), 1u);
+          }
+          mma_commit(&empty[s]);
+          if (c == nchunks - 1) mma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue: warp = (column group cg, TMEM lane quarter wq)
+    const int wq = warp & 3, cg = warp >> 2;
+    const float eps = 1e-6f;
+    const float keps = (float)a.dim * eps * eps;
+    uint32_t tl = 0;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      int ti, tj, nt;
+      cur.seek(a, t, ti, tj, nt);
+      const int64_t n0 = a.gptr[cur.w], n = a.gptr[cur.w + 1] - n0;
+      float* D = a.dense + a.doff[cur.w];
+      int64_t li = (int64_t)ti * TS + wq * 32 + lane;
+      const bool valid = li < n;
+      if (!valid) li = n - 1;
+      const float na = a.norm2[n0 + li], sa = a.sum1[n0 + li];
+      const int fi = (int)a.frame[n0 + li];
+      // this lane's column of the warp's 32-column group (values are exchanged with shuffles below)
+      const int64_t lc = (int64_t)tj * TS + cg * 32 + lane;
+      const bool vc = lc < n;
+      const float nb_l = vc ? a.norm2[n0 + lc] : 0.f, sb_l = vc ? a.sum1[n0 + lc] : 0.f;
+      const int fb_l = vc ? (int)a.frame[n0 + lc] : INT_MIN;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      uint32_t acc0[16], acc1[16];
+      const uint32_t taddr = tcol + buf * TS + cg * 32 + ((uint32_t)(wq * 32) << 16);
+      tmem_ld16(taddr, acc0);
+      tmem_ld16(taddr + 16, acc1);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);             // the accumulator may be overwritten from here on
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float nb = __shfl_sync(0xffffffffu, nb_l, j), sb = __shfl_sync(0xffffffffu, sb_l, j);
+        const int fj = __shfl_sync(0xffffffffu, fb_l, j);
+        const int64_t lj = (int64_t)tj * TS + cg * 32 + j;
+        if (!valid || lj >= n || lj == li) continue;
+        int df = fi - fj; df = df < 0 ? -df : df;
+        const bool conn = fj != INT_MIN && df > 0 && (a.max_dist < 0 || df <= a.max_dist);
+        // ||a_lo - a_hi + eps||^2 with lo / hi = the smaller / larger node index of the pair (the reference's i < j)
+        const float ds = li < lj ? sa - sb : sb - sa;
+        const float d2 = na + nb - 2.f * __uint_as_float(j < 16 ? acc0[j] : acc1[j - 16]) + 2.f * eps * ds + keps;
+        D[lj * n + li] = conn ? sqrtf(fmaxf(d2, 0.f)) : INFINITY;   // row lj, column li: lanes = consecutive floats
+      }
+      if (ti == tj && cg == 0 && valid) D[li * n + li] = INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(*tmem_slot);
 }
 
 }  // namespace gram
 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim) {
   return align_up(total_tiles * (dim / gram::KC) * gram::CHUNK_BYTES, 256) + 2 * align_up(num_nodes * 4, 256) +
-         align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + 1024;
+         2 * align_up((num_graphs + 1) * 8, 256) + align_up(num_nodes * 4, 256) + 1024;
 }
 
 // Fills the dense blocks with Gram distances, ranks, then repairs ambiguous rows exactly.
@@ -316,26 +482,43 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
   float* norm2 = cv.take<float>(n);
   float* sum1 = cv.take<float>(n);
   int64_t* tile_off = cv.take<int64_t>(num_graphs + 1);
+  int64_t* tri_off = cv.take<int64_t>(num_graphs + 1);
   int32_t* amb = cv.take<int32_t>(n + 1);
   MPN_CUDA(cudaMemsetAsync(img, 0, total_tiles * (dim / KC) * CHUNK_BYTES, s));
   MPN_CUDA(cudaMemsetAsync(amb + n, 0, 4, s));
-  tile_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, tile_off); count_launch();
+  tile_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, tile_off, tri_off); count_launch();
   pack_reid_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16), 256, 0, s>>>(
-      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1); count_launch();
+      reid, dim, gptr, num_graphs, tile_off, n, img, norm2, sum1, status); count_launch();
   static bool attr_set = false;
   if (!attr_set) {
     MPN_CUDA(cudaFuncSetAttribute(gram_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MPN_CUDA(cudaFuncSetAttribute(gram_blocks2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
     attr_set = true;
   }
-  GramArgs a;
-  a.reid = reid; a.dim = dim; a.frame = frame; a.gptr = gptr; a.doff = doff; a.tile_off = tile_off;
-  a.img = img; a.norm2 = norm2; a.sum1 = sum1; a.max_dist = max_dist; a.dense = dense; a.status = status;
-  const int64_t ntri = max_tiles * (max_tiles + 1) / 2;
-  int64_t ctas_x = ceil_div(ntri, 2);
-  const int64_t want = ceil_div((int64_t)sm_count(), num_graphs);          // ~1 CTA per SM over the whole batch
-  if (ctas_x > want) ctas_x = want > 0 ? want : 1;
-  dim3 grid((unsigned)ctas_x, (unsigned)num_graphs);
-  gram_blocks_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a); count_launch();
+  static const bool old_kernel = getenv("MPN_GRAM_VARIANT") != nullptr && getenv("MPN_GRAM_VARIANT")[0] == '1';
+  if (!old_kernel) {
+    int64_t total_tri = 0;
+    for (int64_t g = 0; g < num_graphs; ++g) {
+      const int64_t t = ceil_div(h_gptr[g + 1] - h_gptr[g], TS);
+      total_tri += t * t;
+    }
+    Gram2Args a2;
+    a2.frame = frame; a2.gptr = gptr; a2.doff = doff; a2.tile_off = tile_off; a2.tri_off = tri_off;
+    a2.img = img; a2.norm2 = norm2; a2.sum1 = sum1; a2.num_graphs = num_graphs; a2.max_dist = max_dist; a2.dim = dim;
+    a2.dense = dense;
+    const unsigned grid2 = (unsigned)std::min<int64_t>(std::max<int64_t>(total_tri, 1), (int64_t)sm_count());
+    gram_blocks2_kernel<<<grid2, G2_THREADS, G2_SMEM_BYTES, s>>>(a2); count_launch();
+  } else {
+    GramArgs a;
+    a.reid = reid; a.dim = dim; a.frame = frame; a.gptr = gptr; a.doff = doff; a.tile_off = tile_off;
+    a.img = img; a.norm2 = norm2; a.sum1 = sum1; a.max_dist = max_dist; a.dense = dense; a.status = status;
+    const int64_t ntri = max_tiles * (max_tiles + 1) / 2;
+    int64_t ctas_x = ceil_div(ntri, 2);
+    const int64_t want = ceil_div((int64_t)sm_count(), num_graphs);          // ~1 CTA per SM over the whole batch
+    if (ctas_x > want) ctas_x = want > 0 ? want : 1;
+    dim3 grid((unsigned)ctas_x, (unsigned)num_graphs);
+    gram_blocks_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a); count_launch();
+  }
   MPN_LAUNCH_CHECK();
   *norm2_out = norm2; *amb_out = amb; *amb_count_out = amb + n;
   return MPN_OK;

@@ -123,6 +123,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// TMA bulk copy of a contiguous global range into shared memory; completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // TMA row gather: rows r0..r3 of a 2-D tensor map (box {row length, 1}) -> 4 consecutive tile rows at dst
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, uint64_t* bar, int32_t r0, int32_t r1,
                                             int32_t r2, int32_t r3) {
