@@ -227,11 +227,259 @@ __global__ void knn_pairs_kernel(const float* __restrict__ dense, const int64_t*
   }
 }
 
-__global__ void graph_offsets_kernel(const int64_t* __restrict__ gptr, int64_t num_graphs, int64_t* __restrict__ doff) {
+
+// ------------------------------------------------------------------ fused row select (windows of up to 5,120 nodes)
+// One CTA per node: the row's keys are read ONCE into registers; radix-select of the k-th (key, index), the row of
+// the "is among my k nearest" bit matrix M, and (tensor-core path) the ambiguity test of the approximate distances
+// all come from those registers.  Every row is ranked on ITS OWN entries, so nothing downstream assumes that the
+// distance matrix is symmetric (repaired rows are exact, their mirror entries stay approximate).
+constexpr int SEL_THREADS = 256, SEL_MAX_N = 20 * SEL_THREADS;
+
+template <bool kAmb, int SEL_PER>
+__global__ void __launch_bounds__(SEL_THREADS) row_select_kernel(
+    const float* __restrict__ dense, const int64_t* __restrict__ gptr, int64_t num_graphs, const int64_t* __restrict__ doff,
+    const int64_t* __restrict__ moff, int64_t k, const int32_t* __restrict__ row_mask, uint32_t* __restrict__ thr_key,
+    int32_t* __restrict__ thr_idx, uint32_t* __restrict__ M, const float* __restrict__ norm2,
+    const float* __restrict__ win_nmax, float beta, int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining, s_count;
+  __shared__ int32_t s_found;
+  __shared__ float s_min[SEL_THREADS / 32];
+  const int64_t i = blockIdx.x;
+  if (row_mask != nullptr && row_mask[i] == 0) return;
+  int64_t lo = 0, hi = num_graphs;
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
+  const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0, li = i - n0;
+  const float* rowp = dense + doff[lo] + li * n;
+  const int words = (int)((n + 31) >> 5);
+  uint32_t* mrow = M + moff[lo] + li * words;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t key[SEL_PER];
+#pragma unroll
+  for (int q = 0; q < SEL_PER; ++q) {
+    const int64_t j = tid + q * SEL_THREADS;
+    key[q] = j < n ? order_key_f(rowp[j]) : 0xffffffffu;
+  }
+  uint32_t tau = 0xffffffffu;
+  int32_t found = (int32_t)n;
+  if (k < n) {
+    if (tid == 0) { s_prefix = 0u; s_remaining = (int)k; s_found = -1; }
+    uint32_t mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+#pragma unroll
+      for (int q = 0; q < SEL_PER; ++q)
+        if (tid + q * SEL_THREADS < n && (key[q] & mask) == prefix) atomicAdd(&hist[(key[q] >> shift) & 255u], 1);
+      __syncthreads();
+      if (tid < 32) {
+        int h[8], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { h[q] = hist[8 * lane + q]; tot += h[q]; }
+        int incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += v; }
+        const int rem0 = s_remaining;
+        if (incl >= rem0 && incl - tot < rem0) {                          // exactly one lane
+          int rem = rem0 - (incl - tot), b = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { if (h[q] >= rem) { b = q; break; } rem -= h[q]; }
+          s_remaining = rem;
+          s_prefix = prefix | ((uint32_t)(8 * lane + b) << shift);
+          s_count = h[b];
+        }
+      }
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+    tau = s_prefix;
+    const int need = s_remaining;
+    if (s_count == need) {                                                // no tie straddles the boundary: last equal element
+      int32_t mine = -1;
+#pragma unroll
+      for (int q = 0; q < SEL_PER; ++q)
+        if (tid + q * SEL_THREADS < n && key[q] == tau) mine = tid + q * SEL_THREADS;
+      if (mine >= 0) atomicMax(&s_found, mine);
+    } else if (tid < 32) {                                                // first `need` equal elements in index order
+      int seen = 0;
+      int32_t f = (int32_t)(n - 1);
+      for (int64_t j0 = 0; j0 < n; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool eq = j < n && order_key_f(rowp[j]) == tau;
+        const unsigned m = __ballot_sync(kFullMask, eq);
+        const int c = __popc(m);
+        if (seen + c >= need) {
+          unsigned mm = m;
+          for (int q = 1; q < need - seen; ++q) mm &= mm - 1;
+          f = (int32_t)(j0 + __ffs(mm) - 1);
+          break;
+        }
+        seen += c;
+      }
+      if (lane == 0) s_found = f;
+    }
+    __syncthreads();
+    found = s_found;
+  }
+  if (tid == 0) { thr_key[i] = tau; thr_idx[i] = found; }
+  // row of M and the smallest value left outside the top-k
+  float mn = INFINITY;
+#pragma unroll
+  for (int q = 0; q < SEL_PER; ++q) {
+    const int j = tid + q * SEL_THREADS;
+    if (q * SEL_THREADS < n) {                                            // uniform per warp group
+      const bool in = j < n && (key[q] < tau || (key[q] == tau && j <= found));
+      const unsigned m = __ballot_sync(kFullMask, in);
+      const int w = q * (SEL_THREADS / 32) + warp;
+      if (lane == 0 && w < words) mrow[w] = m;
+      if (kAmb && j < n && !in) {
+        const uint32_t u = (key[q] & 0x80000000u) ? (key[q] & 0x7fffffffu) : ~key[q];
+        mn = fminf(mn, __uint_as_float(u));
+      }
+    }
+  }
+  if (kAmb) {
+    for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, d));
+    if (lane == 0) s_min[warp] = mn;
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 1; q < SEL_THREADS / 32; ++q) mn = fminf(mn, s_min[q]);
+      int flag = 0;
+      if (tau != 0xffffffffu) {
+        const uint32_t u = (tau & 0x80000000u) ? (tau & 0x7fffffffu) : ~tau;
+        const float vk = __uint_as_float(u);
+        if (isfinite(vk) && isfinite(mn)) {
+          const float band = beta * (norm2[i] + win_nmax[lo]);            // absolute error bound on d^2
+          flag = (mn * mn - vk * vk) <= 2.f * band ? 1 : 0;
+        }
+      }
+      amb[i] = flag;
+      if (flag) atomicAdd(amb_count, 1);
+    }
+  }
+}
+
+template <bool kAmb>
+static void launch_row_select(int64_t max_n, int64_t n, cudaStream_t s, const float* dense, const int64_t* gptr, int64_t num_graphs,
+                              const int64_t* doff, const int64_t* moff, int64_t k, const int32_t* row_mask, uint32_t* thr_key,
+                              int32_t* thr_idx, uint32_t* M, const float* norm2, const float* win_nmax, float beta, int32_t* amb,
+                              int32_t* amb_count) {
+  const unsigned g = (unsigned)n;
+#define MPN_SEL(PER)                                                                                                     \
+  row_select_kernel<kAmb, PER><<<g, SEL_THREADS, 0, s>>>(dense, gptr, num_graphs, doff, moff, k, row_mask, thr_key, thr_idx, M, \
+                                                         norm2, win_nmax, beta, amb, amb_count)
+  if (max_n <= 5 * SEL_THREADS) MPN_SEL(5);
+  else if (max_n <= 9 * SEL_THREADS) MPN_SEL(9);
+  else if (max_n <= 12 * SEL_THREADS) MPN_SEL(12);
+  else MPN_SEL(20);
+#undef MPN_SEL
+  count_launch();
+}
+
+__global__ void window_max_kernel(const float* __restrict__ v, const int64_t* __restrict__ gptr, float* __restrict__ out) {
+  __shared__ float s[8];
+  const int64_t a = gptr[blockIdx.x], b = gptr[blockIdx.x + 1];
+  float m = 0.f;
+  for (int64_t j = a + threadIdx.x; j < b; j += blockDim.x) m = fmaxf(m, v[j]);
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, d));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int q = 1; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, s[q]); out[blockIdx.x] = m; }
+}
+
+// MT[j][i] = M[i][j] per window: one warp per 32 x 32 bit tile.
+__global__ void bit_transpose_kernel(const uint32_t* __restrict__ M, uint32_t* __restrict__ MT, const int64_t* __restrict__ gptr,
+                                     const int64_t* __restrict__ moff) {
+  const int64_t w = blockIdx.y;
+  const int64_t n = gptr[w + 1] - gptr[w];
+  const int words = (int)((n + 31) >> 5);
+  const uint32_t* m = M + moff[w];
+  uint32_t* mt = MT + moff[w];
+  const int lane = threadIdx.x & 31;
+  const int64_t tiles = (int64_t)words * words;
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < tiles; t += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int rb = (int)(t / words), cb = (int)(t - (int64_t)rb * words);   // rows 32rb.., bit columns 32cb..
+    const int64_t r = (int64_t)rb * 32 + lane;
+    const uint32_t word = r < n ? m[r * words + cb] : 0u;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const unsigned col = __ballot_sync(kFullMask, (word >> b) & 1u);   // column 32cb + b over rows 32rb..32rb+31
+      if (lane == b) mine = col;
+    }
+    const int64_t c = (int64_t)cb * 32 + lane;
+    if (c < n) mt[c * words + rb] = mine;
+  }
+}
+
+// warp per node i: kept pairs (i, j > i) from the bit matrices, ascending j; kFill=false counts.
+template <bool kFill>
+__global__ void mask_pairs_kernel(const uint32_t* __restrict__ M, const uint32_t* __restrict__ MT, const float* __restrict__ dense,
+                                  const int64_t* __restrict__ gptr, int64_t num_graphs, const int64_t* __restrict__ doff,
+                                  const int64_t* __restrict__ moff, const int64_t* __restrict__ frame, int64_t num_nodes,
+                                  int64_t max_dist, int reciprocal, int64_t* __restrict__ row_cnt_or_start,
+                                  int64_t* __restrict__ out_row, int64_t* __restrict__ out_col, float* __restrict__ out_dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < num_nodes; i += nwarps) {
+    int64_t lo = 0, hi = num_graphs;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
+    const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0, li = i - n0;
+    const int words = (int)((n + 31) >> 5);
+    const uint32_t* mi = M + moff[lo] + li * words;
+    const uint32_t* mti = MT + moff[lo] + li * words;
+    const int64_t fi = frame[i];
+    int64_t cursor = kFill ? row_cnt_or_start[i] : 0;
+    for (int c0 = (int)((li + 1) >> 5); c0 < words; c0 += 32) {
+      const int c = c0 + lane;
+      uint32_t bits = 0u;
+      if (c < words) {
+        bits = reciprocal ? (mi[c] & mti[c]) : (mi[c] | mti[c]);
+        const int64_t jbase = (int64_t)c * 32;
+        if (jbase <= li) bits &= (li - jbase >= 31) ? 0u : (0xffffffffu << (li - jbase + 1));   // j > i only
+        uint32_t rest = bits;
+        while (rest) {                                                  // few bits: drop pairs that are not time-valid
+          const int b = __ffs(rest) - 1;
+          rest &= rest - 1;
+          const int64_t lj = jbase + b;
+          if (lj >= n || !frames_connect(fi, frame[n0 + lj], max_dist)) bits &= ~(1u << b);
+        }
+      }
+      int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += v; }
+      if (kFill) {
+        int64_t pos = cursor + incl - cnt;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int64_t lj = (int64_t)c * 32 + b;
+          out_row[pos] = i;
+          out_col[pos] = n0 + lj;
+          out_dist[pos] = dense[doff[lo] + li * n + lj];
+          ++pos;
+        }
+      }
+      cursor += __shfl_sync(kFullMask, incl, 31);
+    }
+    if (!kFill && lane == 0) row_cnt_or_start[i] = cursor;
+  }
+}
+
+__global__ void graph_offsets_kernel(const int64_t* __restrict__ gptr, int64_t num_graphs, int64_t* __restrict__ doff,
+                                     int64_t* __restrict__ moff) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int64_t acc = 0;
-    for (int64_t g = 0; g < num_graphs; ++g) { doff[g] = acc; const int64_t n = gptr[g + 1] - gptr[g]; acc += n * n; }
+    int64_t acc = 0, macc = 0;
+    for (int64_t g = 0; g < num_graphs; ++g) {
+      const int64_t n = gptr[g + 1] - gptr[g];
+      doff[g] = acc; acc += n * n;
+      moff[g] = macc; macc += n * ((n + 31) >> 5);                      // words of the window's bit matrices
+    }
     doff[num_graphs] = acc;
+    moff[num_graphs] = macc;
   }
 }
 
@@ -250,7 +498,7 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
                        int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
                        const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
-                       cudaStream_t s);
+                       int detect, cudaStream_t s);
 
 }  // namespace mpn
 
@@ -259,8 +507,10 @@ using namespace mpn;
 extern "C" {
 
 int64_t mpn_knn_graph_workspace(int64_t num_nodes, int64_t sum_sq_nodes, int64_t num_graphs) {
-  const int64_t base = align_up(sum_sq_nodes * 4, 256) + align_up((num_graphs + 1) * 8, 256) +
-                       2 * align_up(num_nodes * 4, 256) + align_up((num_nodes + 1) * 8, 256) + 2048;
+  const int64_t mask_words = sum_sq_nodes / 32 + num_nodes + 32;       // >= sum_g n_g * ceil(n_g / 32)
+  const int64_t base = align_up(sum_sq_nodes * 4, 256) + 2 * align_up((num_graphs + 1) * 8, 256) +
+                       2 * align_up(num_nodes * 4, 256) + align_up((num_nodes + 1) * 8, 256) +
+                       2 * align_up(mask_words * 4, 256) + align_up(num_graphs * 4, 256) + 2048;
   // tensor-core path: packed fp16 hi/lo image of the embeddings (dim <= 512 covered) + per-node scalars
   return base + gram_workspace_bytes(num_nodes, num_nodes / 128 + num_graphs, num_graphs, 512) + 256;
 }
@@ -286,6 +536,12 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   Carver cv(ws);
   float* dense = cv.take<float>(sum_sq);
   int64_t* doff = cv.take<int64_t>(num_graphs + 1);
+  int64_t* moff = cv.take<int64_t>(num_graphs + 1);
+  int64_t mask_words = 0;
+  for (int64_t g = 0; g < num_graphs; ++g) { const int64_t ng = h_gptr[g + 1] - h_gptr[g]; mask_words += ng * ((ng + 31) >> 5); }
+  uint32_t* M = cv.take<uint32_t>(mask_words + 32);
+  uint32_t* MT = cv.take<uint32_t>(mask_words + 32);
+  float* win_nmax = cv.take<float>(num_graphs);
   uint32_t* tk = cv.take<uint32_t>(n);
   int32_t* ti = cv.take<int32_t>(n);
   int64_t* row_start = cv.take<int64_t>(n + 1);
@@ -300,7 +556,7 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   int rc = MPN_OK;
   MPN_CUDA(cudaMemsetAsync(status, 0, 16, s));
 
-  graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff); count_launch();
+  graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff, moff); count_launch();
   if (tc) {
     rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
                           static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, s);
@@ -310,18 +566,42 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
     dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)num_graphs);
     dist_blocks_kernel<<<grid, 256, 0, s>>>(reid, dim, frame, gptr, doff, max_frame_dist, dense); count_launch();
   }
-  if (prune) {
-    batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti); count_launch();
-    if (tc) {                                                       // repair rows whose top-k set is not certain
-      rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
-                              amb, amb_count, s);
-      if (rc) return rc;
-      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti); count_launch();
-    }
-  }
   const unsigned wgrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 16);
-  knn_pairs_kernel<false><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
-                                               reciprocal, row_start, nullptr, nullptr, nullptr); count_launch();
+  // windows of up to SEL_MAX_N nodes: fused row select -> bit matrices -> pairs; larger windows: the general kernels
+  const bool fused = prune && max_n <= SEL_MAX_N;
+  if (fused) {
+    if (tc) {
+      window_max_kernel<<<(unsigned)num_graphs, 256, 0, s>>>(norm2, gptr, win_nmax); count_launch();
+      launch_row_select<true>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, nullptr, tk, ti, M, norm2, win_nmax, 2e-6f,
+                              amb, amb_count);
+      // rows whose top-k set is not certain: exact fp32 distances, ranked again
+      rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
+                              amb, amb_count, 0, s);
+      if (rc) return rc;
+      launch_row_select<false>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, amb, tk, ti, M, nullptr, nullptr, 0.f,
+                               nullptr, nullptr);
+    } else {
+      launch_row_select<false>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, nullptr, tk, ti, M, nullptr, nullptr, 0.f,
+                               nullptr, nullptr);
+    }
+    const int64_t max_words = (max_n + 31) >> 5;
+    const unsigned tgrid = (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(max_words * max_words * 32, 256), 1), 4096);
+    bit_transpose_kernel<<<dim3(tgrid, (unsigned)num_graphs), 256, 0, s>>>(M, MT, gptr, moff); count_launch();
+    mask_pairs_kernel<false><<<wgrid, 256, 0, s>>>(M, MT, dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
+                                                  row_start, nullptr, nullptr, nullptr); count_launch();
+  } else {
+    if (prune) {
+      batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti); count_launch();
+      if (tc) {                                                       // repair rows whose top-k set is not certain
+        rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
+                                amb, amb_count, 1, s);
+        if (rc) return rc;
+        batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti); count_launch();
+      }
+    }
+    knn_pairs_kernel<false><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
+                                                 reciprocal, row_start, nullptr, nullptr, nullptr); count_launch();
+  }
   MPN_LAUNCH_CHECK();
   rc = exclusive_scan_i64(row_start, row_start, n, s);
   if (rc) return rc;
@@ -341,8 +621,13 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
     set_error("knn_graph_pairs: %lld pairs exceed the output capacity %lld", (long long)total, (long long)capacity);
     return MPN_ENOSPC;
   }
-  knn_pairs_kernel<true><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
-                                              reciprocal, row_start, out_row, out_col, out_dist); count_launch();
+  if (fused) {
+    mask_pairs_kernel<true><<<wgrid, 256, 0, s>>>(M, MT, dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
+                                                 row_start, out_row, out_col, out_dist); count_launch();
+  } else {
+    knn_pairs_kernel<true><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,
+                                                reciprocal, row_start, out_row, out_col, out_dist); count_launch();
+  }
   MPN_LAUNCH_CHECK();
   if (tc && total > 0)                                              // the edge feature is always the exact distance
     return mpn_pair_reid_dist(reid, n, dim, out_row, out_col, total, out_dist, stream);

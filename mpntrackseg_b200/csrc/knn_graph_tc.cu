@@ -382,6 +382,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gram_blocks2_kernel(Gram2Args a
     uint32_t it = 0, tl = 0;
     for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      int ti, tj, nt;
+      cur.seek(a, t, ti, tj, nt);
+      // (i, j) and (j, i) are computed by different tiles and must come out BIT-IDENTICAL (row j compares its own
+      // copy of the pair against its own k-th value): the mirrored tile accumulates the same terms in the same order
+      const bool mirrored = ti > tj;
       mbar_wait(&acc_empty[buf], aph ^ 1);                     // the epilogue has drained this accumulator
       for (int c = 0; c < nchunks; ++c, ++it) {
         const uint32_t s = it % G2_STAGES, ph = (it / G2_STAGES) & 1;
@@ -395,8 +400,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gram_blocks2_kernel(Gram2Args a
             const uint64_t ah = dbase + (uint64_t)((ab + ks * SLAB) >> 4), al = dbase + (uint64_t)((ab + (KC / 16 + ks) * SLAB) >> 4);
             const uint64_t bh = dbase + (uint64_t)((bb + ks * SLAB) >> 4), bl = dbase + (uint64_t)((bb + (KC / 16 + ks) * SLAB) >> 4);
             mma_ss(d, ah, bh, idesc_f16(128, TS), (c > 0 || ks > 0) ? 1u : 0u);
-            mma_ss(d, ah, bl, idesc_f16(128, TS), 1u);
-            mma_ss(d, al, bh, idesc_f16(128, TS), 1u);
+            mma_ss(d, mirrored ? al : ah, mirrored ? bh : bl, idesc_f16(128, TS), 1u);
+            mma_ss(d, mirrored ? ah : al, mirrored ? bl : bh, idesc_f16(128, TS), 1u);
           }
           mma_commit(&empty[s]);
           if (c == nchunks - 1) mma_commit(&acc_full[buf]);
@@ -441,13 +446,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gram_blocks2_kernel(Gram2Args a
         const float nb = __shfl_sync(0xffffffffu, nb_l, j), sb = __shfl_sync(0xffffffffu, sb_l, j);
         const int fj = __shfl_sync(0xffffffffu, fb_l, j);
         const int64_t lj = (int64_t)tj * TS + cg * 32 + j;
-        if (!valid || lj >= n || lj == li) continue;
+        if (!valid || lj >= n || lj == li || (ti == tj && lj < li)) continue;   // diagonal tile: upper half, mirrored below
         int df = fi - fj; df = df < 0 ? -df : df;
         const bool conn = fj != INT_MIN && df > 0 && (a.max_dist < 0 || df <= a.max_dist);
         // ||a_lo - a_hi + eps||^2 with lo / hi = the smaller / larger node index of the pair (the reference's i < j)
         const float ds = li < lj ? sa - sb : sb - sa;
-        const float d2 = na + nb - 2.f * __uint_as_float(j < 16 ? acc0[j] : acc1[j - 16]) + 2.f * eps * ds + keps;
-        D[lj * n + li] = conn ? sqrtf(fmaxf(d2, 0.f)) : INFINITY;   // row lj, column li: lanes = consecutive floats
+        const float d2 = (na + nb) - 2.f * __uint_as_float(j < 16 ? acc0[j] : acc1[j - 16]) + 2.f * eps * ds + keps;
+        const float v = conn ? sqrtf(fmaxf(d2, 0.f)) : INFINITY;
+        D[lj * n + li] = v;                                        // row lj, column li: lanes = consecutive floats
+        if (ti == tj) D[li * n + lj] = v;
       }
       if (ti == tj && cg == 0 && valid) D[li * n + li] = INFINITY;
     }
@@ -527,10 +534,12 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
                        int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
                        const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
-                       cudaStream_t s) {
+                       int detect, cudaStream_t s) {
   using namespace gram;
-  row_ambiguity_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(dense, gptr, num_graphs, doff, norm2, thr_key, thr_idx, beta,
-                                                         amb, amb_count); count_launch();
+  if (detect) {                                                     // (the fused row-select kernel flags rows itself)
+    row_ambiguity_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(dense, gptr, num_graphs, doff, norm2, thr_key, thr_idx, beta,
+                                                           amb, amb_count); count_launch();
+  }
   exact_rows_kernel<<<(unsigned)num_nodes, 256, 0, s>>>(reid, dim, frame, gptr, num_graphs, doff, max_dist, amb, dense);
   count_launch();
   MPN_LAUNCH_CHECK();
