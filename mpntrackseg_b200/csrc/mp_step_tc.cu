@@ -189,17 +189,21 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
 
 // Per step: x' = ReLU(Wn [flow_in | flow_out] + bn)  (models/mpn.py:97-99), then the split copy of
 // x' for the next step's gathers and prow[r] = pinit[r] + W0[:, 32:64] x'.
-__global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
-                                                      int64_t num_nodes, int64_t num_out, int32_t chunks_out,
-                                                      int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
-                                                      const float* __restrict__ node_w, const float* __restrict__ node_b,
-                                                      const float* __restrict__ w0, const float* __restrict__ pinit,
-                                                      __half* __restrict__ xl_next, float* __restrict__ prow,
-                                                      float* __restrict__ x_out, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
+                                                         int64_t num_nodes, int64_t num_out, int32_t chunks_out,
+                                                         int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
+                                                         const float* __restrict__ node_w, const float* __restrict__ node_b,
+                                                         const float* __restrict__ w0, const float* __restrict__ pinit,
+                                                         __half* __restrict__ xl_next, float* __restrict__ prow,
+                                                         float* __restrict__ x_out, int32_t* __restrict__ status) {
+  // Warp per node, lane = output feature.  The lane's column of the node Linear lives in REGISTERS (64 values); a
+  // node's input vector is staged in a per-warp shared-memory buffer and read back as 16-byte broadcasts, so a node
+  // costs ~120 shared-memory instructions instead of 96 shuffles + 160 loads.  The next node's inputs are loaded while the
+  // current one is computed (its row pointers one node earlier), which hides the dependent global round trips.
   __shared__ float s_wn[2 * DN * DN];   // [in][out]
   __shared__ float s_bn[DN];
   __shared__ float s_w0[DN * EH];       // [i][o] over W0 columns 32..63
-  // coalesced global reads (consecutive threads walk a weight row), transposed on the way into smem
+  __shared__ __align__(16) float s_vec[8][96];
   for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
     const int o = idx / (2 * DN), i = idx - o * 2 * DN;
     s_wn[i * DN + o] = node_w[idx];
@@ -213,46 +217,92 @@ __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict_
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float wn[2 * DN];
+#pragma unroll
+  for (int i = 0; i < 2 * DN; ++i) wn[i] = s_wn[i * DN + lane];
+  const int o2 = lane + 64 < EH ? lane + 64 : lane;                    // lanes >= 16 have no third output (result unused)
+  const float bn = s_bn[lane];
+  float* vec = s_vec[threadIdx.x >> 5];
   int ovf = 0;
-  for (int64_t r = warp; r < num_nodes; r += nwarps) {
-    float fl[2];                       // fl[0] = flow_in[lane], fl[1] = flow_out[lane]
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const int32_t* ptr = d == 0 ? in_ptr : out_ptr;
-      const int64_t seg_base = d == 0 ? num_out : 0;
-      const int64_t chunk_off = d == 0 ? chunks_out : 0;
-      const int64_t s0 = ptr[r], s1 = ptr[r + 1];
-      float v = 0.f;
-      if (s1 > s0) {
-        const int64_t ca = (s0 - seg_base) >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
-        if (ca == cb) {
-          v = flow[r * 2 * DN + d * DN + lane];
-        } else {
-          const bool first_in_chunk = ((s0 - seg_base) & ((1 << chunk_shift) - 1)) == 0;
-          v = part[((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN + lane];
-          for (int64_t t = ca + 1; t <= cb; ++t) v += part[((chunk_off + t) * 2) * DN + lane];
-        }
+
+  auto load_ptrs = [&](int64_t r, int32_t* p) { p[0] = in_ptr[r]; p[1] = in_ptr[r + 1]; p[2] = out_ptr[r]; p[3] = out_ptr[r + 1]; };
+  // one direction's flow vector: the row sum written by the edge kernel, or its partials combined in fixed order
+  auto load_flow = [&](int64_t r, int d, int64_t s0, int64_t s1) {
+    const int64_t seg_base = d == 0 ? num_out : 0;
+    const int64_t chunk_off = d == 0 ? chunks_out : 0;
+    float v = 0.f;
+    if (s1 > s0) {
+      const int64_t ca = (s0 - seg_base) >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
+      if (ca == cb) {
+        v = flow[r * 2 * DN + d * DN + lane];
+      } else {
+        const bool first_in_chunk = ((s0 - seg_base) & ((1 << chunk_shift) - 1)) == 0;
+        // the partials of up to four granules are loaded together (independent loads), then added in granule order
+        const int more = (int)(cb - ca);
+        const float* pp = part + ((chunk_off + ca + 1) * 2) * DN + lane;
+        const float v0 = part[((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN + lane];
+        const float v1 = pp[0];
+        const float v2 = more >= 2 ? pp[2 * DN] : 0.f;
+        const float v3 = more >= 3 ? pp[4 * DN] : 0.f;
+        v = v0 + v1;
+        if (more >= 2) v += v2;
+        if (more >= 3) v += v3;
+        for (int64_t t = ca + 4; t <= cb; ++t) v += part[((chunk_off + t) * 2) * DN + lane];
       }
-      fl[d] = v;
     }
-    float acc = s_bn[lane];
+    return v;
+  };
+  auto load_inputs = [&](int64_t r, const int32_t* p, float* fl, float* pin) {
+    fl[0] = load_flow(r, 0, p[0], p[1]);                                // flow_in
+    fl[1] = load_flow(r, 1, p[2], p[3]);                                // flow_out
 #pragma unroll
-    for (int d = 0; d < 2; ++d)
+    for (int q = 0; q < 3; ++q) { const int o = lane + 32 * q; pin[q] = o < EH ? pinit[r * EH + o] : 0.f; }
+  };
+
+  int64_t r = warp;
+  float fl[2] = {0.f, 0.f}, pin[3] = {0.f, 0.f, 0.f};
+  int32_t pn[4] = {0, 0, 0, 0};
+  if (r < num_nodes) {
+    int32_t p[4];
+    load_ptrs(r, p);
+    load_inputs(r, p, fl, pin);
+    if (r + nwarps < num_nodes) load_ptrs(r + nwarps, pn);
+  }
+  for (; r < num_nodes; r += nwarps) {
+    const int64_t r1 = r + nwarps, r2 = r1 + nwarps;
+    float nfl[2] = {0.f, 0.f}, npin[3] = {0.f, 0.f, 0.f};
+    int32_t p2[4] = {0, 0, 0, 0};
+    if (r1 < num_nodes) load_inputs(r1, pn, nfl, npin);
+    if (r2 < num_nodes) load_ptrs(r2, p2);
+
+    vec[lane] = fl[0];
+    vec[DN + lane] = fl[1];
+    __syncwarp();
+    float acc = bn;
 #pragma unroll
-      for (int i = 0; i < DN; ++i) acc = fmaf(__shfl_sync(0xffffffffu, fl[d], i), s_wn[(d * DN + i) * DN + lane], acc);
+    for (int i = 0; i < 2 * DN / 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(vec + 4 * i);
+      acc = fmaf(v.x, wn[4 * i], acc);
+      acc = fmaf(v.y, wn[4 * i + 1], acc);
+      acc = fmaf(v.z, wn[4 * i + 2], acc);
+      acc = fmaf(v.w, wn[4 * i + 3], acc);
+    }
     const float xn = fmaxf(acc, 0.f);
+    vec[2 * DN + lane] = xn;
+    __syncwarp();
     if (x_out != nullptr) x_out[r * DN + lane] = xn;
     store_split_row(xl_next + r * 64, lane, xn, &ovf);
-    float a[3];
+    float a[3] = {pin[0], pin[1], pin[2]};
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { const int o = lane + 32 * q; a[q] = o < EH ? pinit[r * EH + o] : 0.f; }
+    for (int i = 0; i < DN / 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(vec + 2 * DN + 4 * i);
+      const float* wr = s_w0 + 4 * i * EH;
+      const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < DN; ++i) {
-      const float xv = __shfl_sync(0xffffffffu, xn, i);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int o = lane + 32 * q;
-        if (o < EH) a[q] = fmaf(xv, s_w0[i * EH + o], a[q]);
+      for (int u = 0; u < 4; ++u) {
+        a[0] = fmaf(xs[u], wr[u * EH + lane], a[0]);
+        a[1] = fmaf(xs[u], wr[u * EH + lane + 32], a[1]);
+        a[2] = fmaf(xs[u], wr[u * EH + o2], a[2]);
       }
     }
 #pragma unroll
@@ -260,6 +310,12 @@ __global__ void __launch_bounds__(256) node_tc_kernel(const int32_t* __restrict_
       const int o = lane + 32 * q;
       if (o < EH) prow[r * EH + o] = a[q];
     }
+    __syncwarp();                                                       // vec is rewritten by the next node
+    fl[0] = nfl[0]; fl[1] = nfl[1];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) pin[q] = npin[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pn[q] = p2[q];
   }
   if (ovf) atomicOr(status, 1);
 }
@@ -1228,6 +1284,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   const int sms = sm_count();
   tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, tc::variant() == 3 ? 1 : 0); count_launch();
   const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 4);
+  const unsigned ngrid_node = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 2);   // node weights in registers: 2 CTAs/SM
   tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, status);
   count_launch();
   if (e > 0) {
@@ -1282,7 +1339,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       if (profiling()) profile_mark(0, false, s);
     }
     if (profiling()) profile_mark(1, true, s);
-    tc::node_tc_kernel<<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
+    tc::node_tc_kernel<<<ngrid_node, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
                                              (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
                                              w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
                                              step == num_steps ? x_out : nullptr, status);
