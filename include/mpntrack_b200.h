@@ -87,6 +87,14 @@ int mpn_compact_pairs(const int64_t* row, const int64_t* col, const float* dist,
                       int64_t* out_row, int64_t* out_col, float* out_dist,
                       int64_t* h_kept, void* stream);
 
+/* data/mot_graph.py:223-262 MOTGraph.assign_edge_labels: labels[e] = 1 for directed edges between detections of the
+ * same identity (node_ids, -1 = false positive, never linked); closest != 0 ('closest' mode, the shipped default):
+ * only the edge to the closest same-identity partner (by node index) in the future and in the past of edge_row[e];
+ * closest == 0: 'all'.  workspace: 2 * num_nodes int32.  num_nodes < 2^31 - 1. */
+int mpn_assign_edge_labels(const int64_t* edge_row, const int64_t* edge_col, int64_t num_edges,
+                           const int64_t* node_ids, int64_t num_nodes, int closest, void* workspace,
+                           float* labels, void* stream);
+
 /* utils/graph.py:90-124 compute_edge_feats_dict + data/mot_graph.py:292-312 assembly.
  * For each undirected pair p (row<col) writes the feature row
  *   [dt, dx/hbar, dy/hbar, log(h_col/h_row), log(w_col/w_row), reid_dist]

@@ -44,6 +44,7 @@ SIGNATURES = {
     'mpn_pair_reid_dist': (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'mpn_knn_mask_workspace': (c_i64, [c_i64]),
     'mpn_knn_mask': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    'mpn_assign_edge_labels': (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp]),
     'mpn_compact_pairs': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64p, c_vp]),
     'mpn_edge_feats_assemble': (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32,
                                           c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -354,3 +354,53 @@ int mpn_edge_feats_assemble(const int64_t* row, const int64_t* col, int64_t np, 
 }
 
 }  // extern "C"
+
+namespace mpn {
+// Edge labels of the network-flow formulation (data/mot_graph.py:223-262).  'closest': a directed edge (r -> c) between
+// two detections of the same identity is active iff c is r's closest same-identity partner (by node index) among its
+// later (c > r) resp. earlier (c < r) neighbours.  Index distances to distinct partners are distinct, so the reference's
+// arg-min has no ties; the minimum is found with integer atomics (order independent).
+__global__ void label_extrema_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t num_edges,
+                                     const int64_t* __restrict__ ids, int32_t* __restrict__ fut, int32_t* __restrict__ past) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row[e], c = col[e];
+    const int64_t a = ids[r];
+    if (a == -1 || a != ids[c]) continue;
+    if (c > r) atomicMin(&fut[r], (int32_t)c);
+    else if (c < r) atomicMax(&past[r], (int32_t)c);
+  }
+}
+
+__global__ void label_assign_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t num_edges,
+                                    const int64_t* __restrict__ ids, const int32_t* __restrict__ fut,
+                                    const int32_t* __restrict__ past, int closest, float* __restrict__ labels) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row[e], c = col[e];
+    const int64_t a = ids[r];
+    bool on = a != -1 && a == ids[c];
+    if (on && closest) on = c > r ? fut[r] == (int32_t)c : (c < r && past[r] == (int32_t)c);
+    labels[e] = on ? 1.f : 0.f;
+  }
+}
+}  // namespace mpn
+
+extern "C" int mpn_assign_edge_labels(const int64_t* edge_row, const int64_t* edge_col, int64_t num_edges,
+                                      const int64_t* node_ids, int64_t num_nodes, int closest, void* workspace,
+                                      float* labels, void* stream) {
+  using namespace mpn;
+  MPN_CHECK_ARG(num_edges >= 0 && num_nodes >= 0 && num_nodes < 2147483647LL, "assign_edge_labels: bad sizes");
+  if (num_edges == 0) return MPN_OK;
+  MPN_CHECK_ARG(edge_row && edge_col && node_ids && labels && workspace, "assign_edge_labels: null argument");
+  cudaStream_t s = as_stream(stream);
+  int32_t* fut = static_cast<int32_t*>(workspace);
+  int32_t* past = fut + num_nodes;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(num_edges, 256), (int64_t)sm_count() * 8);
+  if (closest) {
+    MPN_CUDA(cudaMemsetAsync(fut, 0x7f, sizeof(int32_t) * num_nodes, s));      // 0x7f7f7f7f > any node index
+    MPN_CUDA(cudaMemsetAsync(past, 0xff, sizeof(int32_t) * num_nodes, s));     // -1
+    label_extrema_kernel<<<grid, 256, 0, s>>>(edge_row, edge_col, num_edges, node_ids, fut, past); count_launch();
+  }
+  label_assign_kernel<<<grid, 256, 0, s>>>(edge_row, edge_col, num_edges, node_ids, fut, past, closest, labels); count_launch();
+  MPN_LAUNCH_CHECK();
+  return MPN_OK;
+}

@@ -145,6 +145,15 @@ class MOTGraph(object):
         return self.graph_obj
 
 
+    def assign_edge_labels(self):
+        """graph_obj.edge_labels [E] float per dataset_params['true_edge_labels'] ('closest' | 'all') from the
+        ``id`` column of the detection table.  reference: data/mot_graph.py:223-262"""
+        mode = self.dataset_params.get('true_edge_labels', 'closest')
+        ids = _col(self.graph_df, 'id', self.device).to(torch.int64)
+        self.graph_obj.edge_labels = ops.assign_edge_labels(self.graph_obj.edge_index, ids, mode)
+        return self.graph_obj.edge_labels
+
+
 class GraphBatch(object):
     """Block-diagonal batch of independent window graphs built in one pass (extension; the
     reference builds one window per ``MOTGraph``).  Node / edge ids are batch-global:

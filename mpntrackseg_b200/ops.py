@@ -75,6 +75,20 @@ def knn_mask(pwise_dist, edge_ixs, num_nodes, top_k, reciprocal, symmetric_edges
     return keep.view(torch.bool)
 
 
+def assign_edge_labels(edge_index, node_ids, mode='closest'):
+    """Float labels [E] of the network-flow formulation.  data/mot_graph.py:223-262"""
+    if mode not in ('all', 'closest'):
+        raise ValueError(f"true_edge_labels must be 'all' or 'closest', got {mode!r}")
+    ei = _req(edge_index, torch.int64, 'edge_index')
+    ids = _req(node_ids, torch.int64, 'node_ids')
+    e, n = ei.shape[1], ids.numel()
+    ws = torch.empty(max(2 * n, 1), dtype=torch.int32, device=ei.device)
+    labels = torch.empty(e, dtype=torch.float32, device=ei.device)
+    check(lib().mpn_assign_edge_labels(ptr(ei[0]), ptr(ei[1]), e, ptr(ids), n, 1 if mode == 'closest' else 0, ptr(ws),
+                                       ptr(labels), stream_ptr()), 'assign_edge_labels')
+    return labels
+
+
 def compact_pairs(pairs, keep, dist=None):
     """pairs[:, keep] (and dist[keep]) in order.  data/mot_graph.py:219"""
     pairs = _req(pairs, torch.int64, 'pairs')

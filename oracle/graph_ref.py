@@ -120,3 +120,29 @@ def prune_window(edge_index, edge_attr, reid_emb_dists, num_nodes, dataset_param
                          reciprocal_k_nns=dataset_params['reciprocal_k_nns'],
                          symmetric_edges=True)
     return edge_index[:, keep], edge_attr[keep], keep
+
+
+def assign_edge_labels(edge_index, node_ids, mode='closest'):
+    """Edge labels of the network-flow formulation: 1 for directed edges between detections of the same
+    identity (-1 = false positive, never linked); 'closest' keeps, per source node, only the edge to the
+    same-identity partner that is closest by node index among its later resp. earlier neighbours
+    (scatter_min arg-min per node and direction).  reference: data/mot_graph.py:223-262"""
+    ids = torch.as_tensor(node_ids).long()
+    r, c = edge_index[0].long(), edge_index[1].long()
+    same = (ids[r] == ids[c]) & (ids[r] != -1)
+    labels = torch.zeros(edge_index.shape[1])
+    if mode == 'all':
+        labels[same] = 1
+        return labels
+    n = ids.numel()
+    for future in (True, False):
+        m = same & ((r < c) if future else (r > c))
+        dist = (r - c).abs()
+        best = {}
+        for e in torch.nonzero(m).view(-1).tolist():                # first minimum wins, as scatter_min's arg-min
+            k = int(r[e])
+            if k not in best or int(dist[e]) < best[k][0]:
+                best[k] = (int(dist[e]), e)
+        for _, e in best.values():
+            labels[e] = 1
+    return labels

@@ -192,6 +192,39 @@ def run_tracker_case():
         param_checksum=checksum(*P.values()))
 
 
+def run_edge_labels_case():
+    """Edge labels ('closest' and 'all') of the config1 training graph, computed the way
+    MOTGraph.assign_edge_labels does (reference: data/mot_graph.py:228-259) with the torch_scatter stand-in's
+    scatter_min; every 7th detection is turned into a false positive (id -1)."""
+    from torch_scatter import scatter_min
+    c = CASES['config1']
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    _, edge_index, _, _ = ref_build_graph(win, ds, False, c.get('max_frame_dist', 'max'))
+    ids = win.ident.clone().long()
+    ids[::7] = -1
+    per_edge_ids = torch.stack([ids[edge_index[0]], ids[edge_index[1]]])                      # :230
+    same_id = (per_edge_ids[0] == per_edge_ids[1]) & (per_edge_ids[0] != -1)                  # :231
+    out = {}
+    lab_all = torch.zeros_like(same_id, dtype=torch.float)
+    lab_all[same_id] = 1                                                                      # :235
+    out['labels_all'] = lab_all.numpy()
+    labels = torch.zeros_like(same_id, dtype=torch.float)
+    same_ids_ixs = torch.where(same_id)
+    se = edge_index.T[same_id].T
+    time_dists = torch.abs(se[0] - se[1])                                                     # :240
+    active = torch.zeros(se.shape[1], dtype=torch.bool)
+    for mask in (se[0] < se[1], se[0] > se[1]):                                               # :243, :252
+        arg = scatter_min(time_dists[mask], se[0][mask], dim=0, dim_size=win.N)[1]            # :244-245, :253-254
+        orig = torch.cat((se[1][mask], torch.as_tensor([-1])))                                # :246-247
+        active |= orig[arg][se[0]] == se[1]                                                   # :248-249
+    labels[same_ids_ixs[0][active]] = 1                                                       # :258-259
+    out['labels_closest'] = labels.numpy()
+    print('edge_labels', dict(E=edge_index.shape[1], same_id=int(same_id.sum()), closest=int(labels.sum())))
+    np.savez_compressed(os.path.join(HERE, 'edge_labels.npz'), **out, edge_index=edge_index.numpy().astype(np.int32),
+                        ids=ids.numpy())
+
+
 class _GraphObj:
     """The attribute bag the reference's to_undirected_graph / to_lightweight_graph work on."""
 
@@ -278,3 +311,5 @@ if __name__ == '__main__':
         run_tracker_case()
     if not only or 'tracker_sequence' in only:
         run_tracker_sequence_case()
+    if not only or 'edge_labels' in only:
+        run_edge_labels_case()

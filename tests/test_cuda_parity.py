@@ -160,6 +160,28 @@ def test_tracker_window_prune_and_predict():
     assert float((preds.cpu() - torch.from_numpy(gold['edge_preds'])).abs().max()) <= PROB_TOL
 
 
+def test_assign_edge_labels_against_golden():
+    """MOTGraph.assign_edge_labels (data/mot_graph.py:223-262) on the GPU, both modes, bit-exact."""
+    import os
+    from mpntrackseg_b200 import ops
+    from mpntrackseg_b200.data.mot_graph import Graph, MOTGraph
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'edge_labels.npz')))
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    ids = torch.from_numpy(gold['ids']).to(dev())
+    for mode in ('all', 'closest'):
+        got = ops.assign_edge_labels(ei, ids, mode)
+        assert np.array_equal(got.cpu().numpy(), gold[f'labels_{mode}'])
+    # through the reference-shaped entry point, shuffled edge order
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1)).to(dev())
+    c = load_case('config1')
+    cols = dict(synth.det_columns(c['win']), id=gold['ids'])
+    mg = MOTGraph(cols, c['win'].reid, c['win'].x, None, {'fps': c['win'].fps}, dict(c['ds'], true_edge_labels='closest'))
+    mg.graph_obj = Graph(x=c['win'].x, edge_index=ei[:, perm].contiguous())
+    assert np.array_equal(mg.assign_edge_labels().cpu().numpy(), gold['labels_closest'][perm.cpu().numpy()])
+    with pytest.raises(ValueError):
+        ops.assign_edge_labels(ei, ids, 'nearest')
+
+
 class _FullGraph(object):
     pass
 

@@ -109,6 +109,27 @@ def test_tracker_sequence_sliding_windows():
         assert np.array_equal(lp.numpy(), seq[f'light_preds_{tag}'])
 
 
+def test_edge_labels_against_reference_formulation_and_brute_force():
+    """data/mot_graph.py:223-262: oracle vs the fixture made with the reference's scatter_min data flow, and vs
+    the definition (closest same-identity partner by node index, per direction)."""
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'edge_labels.npz')))
+    ei, ids = torch.from_numpy(gold['edge_index'].astype(np.int64)), torch.from_numpy(gold['ids'])
+    assert np.array_equal(graph_ref.assign_edge_labels(ei, ids, 'all').numpy(), gold['labels_all'])
+    got = graph_ref.assign_edge_labels(ei, ids, 'closest')
+    assert np.array_equal(got.numpy(), gold['labels_closest'])
+    nbrs = {}
+    for e, (r, c) in enumerate(ei.T.tolist()):
+        if ids[r] == ids[c] and ids[r] != -1:
+            nbrs.setdefault((r, c > r), []).append(c)
+    exp = torch.zeros(ei.shape[1])
+    for e, (r, c) in enumerate(ei.T.tolist()):
+        cand = nbrs.get((r, c > r), [])
+        if ids[r] == ids[c] and ids[r] != -1 and c == (min(cand) if c > r else max(cand)):
+            exp[e] = 1
+    assert torch.equal(got, exp)
+    assert 0 < exp.sum() < gold['labels_all'].sum()
+
+
 def test_knn_mask_independent_restatement():
     """The dense-argsort restatement agrees with a per-node sort formulation."""
     win = synth.make_window(T=7, D=9, k=8, seed=5)
