@@ -592,6 +592,33 @@ def test_tensor_core_gram_knn_equals_exact_path_and_repairs_near_ties():
     assert torch.equal(tc.graph(0).edge_index.cpu(), ref['edge_index'])
 
 
+@pytest.mark.parametrize('recip', [True, False])
+def test_knn_graph_pairs_ragged_windows_match_oracle(recip):
+    """Batched builder on ragged windows (1 node, one frame only, sizes around the 32-bit word and 128-row tile
+    boundaries, k above and below the row length) against the oracle, window by window, for both engines.  One
+    window has duplicated embeddings: its distances come in exactly tied groups that sit one ulp apart, where the
+    order depends on the summation order of the distance itself -- there the two engines must agree with each other
+    (the tensor-core path has to repair those rows with the exact kernel's arithmetic)."""
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    shapes = [(1, 1), (1, 6), (2, 1), (3, 11), (5, 13), (9, 15), (4, 65), (7, 37)]      # (T, D): N = 1, 6, 2, 33, 65, 135, 260, 259
+    wins = [synth.make_window(T=t, D=d, k=3, seed=70 + i) for i, (t, d) in enumerate(shapes)]
+    tied = 5
+    wins[tied].reid = wins[tied].reid[torch.arange(wins[tied].N) % 20].contiguous()
+    inputs = [dict(synth.det_columns(w), reid=w.reid, x=w.x) for w in wins]
+    for k in (1, 4, 40, 300):
+        ds = default_dataset_params(top_k_nns=k, frames_per_graph=9, reciprocal_k_nns=recip)
+        tc = build_window_graphs(inputs, ds, fps=30.0, engine='tc')
+        ex = build_window_graphs(inputs, ds, fps=30.0, engine='fp32')
+        assert tc.pair_ptr == ex.pair_ptr and torch.equal(tc.edge_index, ex.edge_index), (recip, k)
+        for g, w in enumerate(wins):
+            if g == tied:
+                continue
+            ref = graph_ref.build_graph(w.frame, w.reid, synth.det_columns(w), w.fps, ds)
+            got = tc.graph(g)
+            assert torch.equal(got.edge_index.cpu(), ref['edge_index']), (recip, k, g, w.N)
+            np.testing.assert_allclose(got.edge_attr.cpu().numpy(), ref['edge_attr'].numpy(), rtol=3e-6, atol=1e-6)
+
+
 def test_tensor_core_gram_config2_window_no_repairs_needed():
     from mpntrackseg_b200 import ops
     from mpntrackseg_b200.data.mot_graph import build_window_graphs
