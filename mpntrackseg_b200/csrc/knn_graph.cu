@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SEL_THREADS) row_select_kernel(
         const float vk = __uint_as_float(u);
         if (isfinite(vk) && isfinite(mn)) {
           const float band = beta * (norm2[i] + win_nmax[lo]);            // absolute error bound on d^2
-          flag = (mn * mn - vk * vk) <= 2.f * band ? 1 : 0;
+          flag = (mn - vk) <= 2.f * band ? 1 : 0;                         // the approximate rows hold d^2
         }
       }
       amb[i] = flag;
@@ -494,7 +494,8 @@ __global__ void graph_pair_ptr_kernel(const int64_t* __restrict__ gptr, int64_t 
 int64_t gram_workspace_bytes(int64_t num_nodes, int64_t total_tiles, int64_t num_graphs, int64_t dim);
 int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
                      int64_t num_graphs, const int64_t* doff, int64_t max_dist, void* ws, float* dense,
-                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, cudaStream_t s);
+                     int32_t* status, float** norm2_out, int32_t** amb_out, int32_t** amb_count_out, int squared,
+                     cudaStream_t s);
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
                        int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
                        const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
@@ -559,7 +560,8 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff, moff); count_launch();
   if (tc) {
     rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
-                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count, s);
+                          static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count,
+                          max_n <= SEL_MAX_N ? 1 : 0, s);
     if (rc) return rc;
   } else {
     const int64_t nt = ceil_div(max_n, DT);
