@@ -16,16 +16,26 @@ __global__ void avgpool_vec_kernel(const float4* __restrict__ x, int64_t rows, f
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r0 = warp * ROWS_PER_WARP; r0 < rows; r0 += nwarps * ROWS_PER_WARP) {
-    const int64_t r = r0 + lane / GROUP;
-    float s = 0.f;
-    if (r < rows) {
-      const float4 v = __ldcs(x + r0 * GROUP + lane);        // streaming: read once
-      s = (v.x + v.y) + (v.z + v.w);
+  // UNROLL independent 16-byte loads per thread are issued before any of them is consumed: the kernel is a pure
+  // HBM stream and needs the bytes in flight (one load per thread left it at 87 % of the measured peak)
+  constexpr int UNROLL = 4;
+  const int64_t stride = nwarps * ROWS_PER_WARP;
+  for (int64_t r0 = warp * ROWS_PER_WARP; r0 < rows; r0 += UNROLL * stride) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t ru = r0 + u * stride;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ru + lane / GROUP < rows) v[u] = __ldcs(x + ru * GROUP + lane);      // streaming: read once
     }
 #pragma unroll
-    for (int d = GROUP / 2; d > 0; d >>= 1) s += __shfl_xor_sync(kFull, s, d);
-    if (r < rows && (lane % GROUP) == 0) out[r] = s / (float)hw;
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t r = r0 + u * stride + lane / GROUP;
+      float s = (v[u].x + v[u].y) + (v[u].z + v[u].w);
+#pragma unroll
+      for (int d = GROUP / 2; d > 0; d >>= 1) s += __shfl_xor_sync(kFull, s, d);
+      if (r < rows && (lane % GROUP) == 0) out[r] = s / (float)hw;
+    }
   }
 }
 
