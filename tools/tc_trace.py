@@ -24,19 +24,8 @@ with torch.no_grad():
     model.forward_batch(graphs)
     lib.mpn_tc_set_trace(None)
 torch.cuda.synchronize()
-if os.environ.get('MPN_TC_VARIANT', '3') == '3':
-    t = buf.cpu().view(16, 2, 32)
-    names3 = ['top', 'cpwait', 'bar', 'issue1+idx', 'dready1', 'epi1', 'pub2', 'dready2', 'epi2+pub3', 'dready3', 'epi3', 'pub4',
-              'dready4', 'epi4', 'pairbar', 'rowsum+fetch']
-    for i in range(2, 10):
-        for h in range(2):
-            row = t[i, h]
-            if row[0] == 0: continue
-            d = [int(row[k] - row[k - 1]) for k in range(1, 16)]
-            print(f'tile {i:2d} half {"AB"[h]} total {int(row[15]-row[0]):6d} | ' + ' '.join(f'{n}:{v}' for n, v in zip(names3[1:], d)))
-            if h == 0:
-                print('      issue L1..L4 (begin->end):', [int(row[17 + 2 * l] - row[16 + 2 * l]) for l in range(4)])
-    sys.exit(0)
+if os.environ.get('MPN_TC_VARIANT', '3') != '2':
+    sys.exit('the cycle trace is instrumented in the previous kernel only: run with MPN_TC_VARIANT=2')
 t = buf.cpu().view(64, 16)
 names = ['start', 'cpasync_wait', 'load->arrive', 'prow issued', 'dready1', 'epi1 done', 'dready2', 'epi2 arrive', 'cls done', 'dready3', 'epi3 done', 'dready4', 'tile end']
 for i in range(2, 12):
