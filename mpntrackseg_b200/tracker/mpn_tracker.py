@@ -10,10 +10,15 @@ B200 design of ``_evaluate_graph_in_batches`` (same results, different schedule)
   * every node of the sequence is encoded ONCE (avg-pool + 2048->128->32 on tcgen05) instead of once per
     window it appears in (``frames_per_graph`` times in the reference) -- the encoder is per node, so the
     values are the same;
-  * a window's candidate edges are found from a row pointer over the (i < j)-sorted pair list (nodes are
-    sorted by frame, so a window is a contiguous node range) instead of masking the whole edge list per window;
+  * when the sequence graph carries its detection table and ReID embeddings (a ``MOTGraph``), the windows of a
+    batch are pruned TOGETHER: their node rows are replicated into one table and the batched builder
+    (``build_graph_batch``: time-valid pairs + distances + KNN + edge features in one pass, one host sync) rebuilds
+    each window's pruned graph -- the same candidate pairs, distances and features the sequence graph holds;
+    the kept pairs are mapped back to sequence edge ids with a binary search over the sorted pair list.
+    Otherwise a window's candidate edges are found from a row pointer over the (i < j)-sorted pair list and pruned
+    window by window with ``get_knn_mask``;
   * windows are evaluated in block-diagonal batches (``MOTMPNet.forward_batch``), predictions are accumulated
-    on the device; nothing returns to the host between windows except the per-window kept-edge counts.
+    on the device.
 The mask branch (``x_ext`` present and the model has the attention / mask modules) is evaluated window by
 window through ``_predict_edges_and_masks`` exactly as the reference does.
 """
@@ -92,6 +97,8 @@ class MPNTracker(object):
         needs_masks = x_ext is not None and getattr(self.graph_model, 'has_mask_branch', False)
         if self.use_gt or pred_oracle_mode is not None or needs_masks or not self._structured(go):
             self._evaluate_window_by_window(pred_oracle_mode)
+        elif self._has_tables():
+            self._evaluate_batched_rebuild()
         else:
             self._evaluate_batched()
         to_undirected_graph(self.full_graph, attrs_to_update=('edge_preds', 'edge_labels'))
@@ -149,6 +156,82 @@ class MPNTracker(object):
         if node_total is not None:
             go.node_preds = node_total / node_count.view(-1, 1, 1, 1)
 
+    _TABLE_COLS = ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')
+
+    def _has_tables(self):
+        mg = self.full_graph
+        df = getattr(mg, 'graph_df', None)
+        try:
+            cols_ok = df is not None and all(c in df for c in self._TABLE_COLS)
+        except TypeError:
+            cols_ok = False
+        return (cols_ok and getattr(mg, 'reid_embeddings', None) is not None and
+                'fps' in (getattr(mg, 'seq_info_dict', None) or {}) and getattr(mg, 'max_frame_dist', None) is not None)
+
+    def _window_node_ranges(self, frame):
+        windows = self._windows()
+        starts = torch.tensor([int(w[0]) for w in windows], device=frame.device)
+        ends = torch.tensor([int(w[1]) for w in windows], device=frame.device)
+        return (torch.searchsorted(frame, starts, right=False).tolist(),
+                torch.searchsorted(frame, ends, right=True).tolist())
+
+    def _evaluate_batched_rebuild(self):
+        """Batched schedule for a sequence graph that still has its detection table and embeddings."""
+        from ..data.mot_graph import build_graph_batch
+        mg = self.full_graph
+        go, model, ds = mg.graph_obj, self.graph_model, self.dataset_params
+        dev = go.edge_index.device
+        frame = self._frame_per_node(dev)
+        assert bool((frame[1:] >= frame[:-1]).all()), 'nodes must be sorted by frame (mot_graph.py:145)'
+        n, half = go.num_nodes, go.num_edges // 2
+        keys = go.edge_index[0, :half] * n + go.edge_index[1, :half]                  # ascending (checked by _structured)
+        df = mg.graph_df
+        col = lambda c: torch.as_tensor(np.asarray(df[c].values if hasattr(df[c], 'values') else df[c])).to(dev)
+        cols = {c: col(c) for c in self._TABLE_COLS}
+        reid = mg.reid_embeddings.to(dev, torch.float32)
+        with torch.no_grad():
+            x_enc = model.encode_nodes(go.x)                                          # every node once
+        total = torch.zeros(2 * half, device=dev)
+        count = torch.zeros(2 * half, device=dev)
+        all_inactive = bool(self.eval_params['set_pruned_edges_to_inactive'])
+        n0s, n1s = self._window_node_ranges(frame)
+        for b0 in range(0, len(n0s), self.window_batch):
+            rng = list(zip(n0s[b0:b0 + self.window_batch], n1s[b0:b0 + self.window_batch]))
+            idx = torch.cat([torch.arange(a, b, device=dev) for a, b in rng])         # sequence node id of every batch row
+            node_ptr = [0]
+            for a, b in rng:
+                node_ptr.append(node_ptr[-1] + (b - a))
+            table = {c: v[idx] for c, v in cols.items()}
+            table['reid'], table['x'] = reid[idx], x_enc[idx]
+            batch = build_graph_batch(table, node_ptr, ds, mg.seq_info_dict['fps'], inference_mode=False,
+                                      max_frame_dist=mg.max_frame_dist, device=dev)
+            pairs = batch.pair_ptr[-1]
+            if pairs == 0:
+                continue
+            with torch.no_grad():
+                out = model.forward_batch(batch, encoded=True)
+            probs = torch.sigmoid(out.logits[-1]).float()
+            gi, gj = idx[batch.edge_index[0, :pairs]], idx[batch.edge_index[1, :pairs]]
+            ids = torch.searchsorted(keys, gi * n + gj)                                # exact hits: same candidate pairs
+            total.index_add_(0, ids, probs[:pairs])
+            total.index_add_(0, ids + half, probs[pairs:])
+            if not all_inactive:
+                one = torch.ones(pairs, device=dev)
+                count.index_add_(0, ids, one)
+                count.index_add_(0, ids + half, one)
+        if all_inactive:
+            # every window that contains both endpoints predicts the edge (pruned ones as 0): windows t with
+            # t <= f_i and f_j <= t + fpg - 1, f = frame position in the sequence's frame list
+            all_frames = torch.as_tensor(np.array(mg.frames)).to(dev, frame.dtype)
+            fpos = torch.searchsorted(all_frames, frame)
+            fi, fj = fpos[go.edge_index[0, :half]], fpos[go.edge_index[1, :half]]
+            fpg, nwin = mg.frames_per_graph, len(n0s)
+            c = (torch.minimum(fi, torch.full_like(fi, nwin - 1)) - (fj - fpg + 1).clamp(min=0) + 1).clamp(min=0).float()
+            count = torch.cat((c, c))
+        final = total / count
+        final[torch.isnan(final)] = 0
+        go.edge_preds = final
+
     def _evaluate_batched(self):
         go = self.full_graph.graph_obj
         model = self.graph_model
@@ -170,12 +253,8 @@ class MPNTracker(object):
         total = torch.zeros(2 * half, device=dev)
         count = torch.zeros(2 * half, device=dev)
         all_inactive = bool(self.eval_params['set_pruned_edges_to_inactive'])
-        windows = self._windows()
-        starts = torch.tensor([int(w[0]) for w in windows], device=dev)
-        ends = torch.tensor([int(w[1]) for w in windows], device=dev)
-        n0s = torch.searchsorted(frame, starts, right=False).tolist()
-        n1s = torch.searchsorted(frame, ends, right=True).tolist()
-        for b0 in range(0, len(windows), self.window_batch):
+        n0s, n1s = self._window_node_ranges(frame)
+        for b0 in range(0, len(n0s), self.window_batch):
             graphs, ids_kept = [], []
             for n0, n1 in zip(n0s[b0:b0 + self.window_batch], n1s[b0:b0 + self.window_batch]):
                 # pairs of row i start at rowptr[i] with j = jfirst[i], jfirst[i] + 1, ... : keep those with j < n1

@@ -186,21 +186,24 @@ class _FullGraph(object):
     pass
 
 
-def _sequence_full_graph(c):
+def _sequence_full_graph(c, with_tables=True):
     from mpntrackseg_b200.data.mot_graph import MOTGraph
     win, ds = c['win'], c['ds']
     mg = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
                   max_frame_dist=ds['frames_per_graph'] - 1)
     mg.construct_graph_object()
-    full = _FullGraph()
-    full.graph_obj, full.graph_df = mg.graph_obj, synth.det_columns(win)
+    if with_tables:                                            # the MOTGraph itself: detection table + embeddings available
+        full = mg
+    else:
+        full = _FullGraph()
+        full.graph_obj, full.graph_df = mg.graph_obj, {'frame': synth.det_columns(win)['frame']}
     full.frames = sorted(set(win.frame.tolist()))
     full.frames_per_graph = ds['frames_per_graph']
     return full
 
 
 @pytest.mark.parametrize('inactive', [False, True])
-@pytest.mark.parametrize('schedule', ['batched', 'window_by_window'])
+@pytest.mark.parametrize('schedule', ['batched_rebuild', 'batched', 'window_by_window'])
 def test_tracker_sequence_sliding_windows(inactive, schedule):
     """MPNTracker._evaluate_graph_in_batches (mpn_tracker.py:143-210) -- batched B200 schedule and the
     reference's window-by-window schedule -- against the reference's golden sequence output."""
@@ -211,10 +214,13 @@ def test_tracker_sequence_sliding_windows(inactive, schedule):
     tag = 'inactive' if inactive else 'knn'
     tracker = MPNTracker(dataset=None, graph_model=make_model(c['mp'], c['P']), use_gt=False,
                          eval_params={'set_pruned_edges_to_inactive': inactive}, dataset_params=c['ds'], window_batch=2)
-    tracker.full_graph = _sequence_full_graph(c)
+    tracker.full_graph = _sequence_full_graph(c, with_tables=schedule == 'batched_rebuild')
     go = tracker.full_graph.graph_obj
-    if schedule == 'batched':
+    assert tracker._has_tables() == (schedule == 'batched_rebuild')
+    if schedule == 'batched_rebuild':
         assert tracker._structured(go)
+        tracker._evaluate_batched_rebuild()
+    elif schedule == 'batched':
         tracker._evaluate_batched()
     else:
         tracker._evaluate_window_by_window(None)

@@ -29,11 +29,9 @@ def full_graph(win, ds):
     mg = MOTGraph(synth.det_columns(win), win.reid, win.x.to(dev), None, {'fps': win.fps}, ds, inference_mode=True,
                   max_frame_dist=FPG - 1)
     mg.construct_graph_object()
-    f = Full()
-    f.graph_obj, f.graph_df = mg.graph_obj, synth.det_columns(win)
-    f.frames = sorted(set(win.frame.tolist()))
-    f.frames_per_graph = FPG
-    return f
+    mg.frames = sorted(set(win.frame.tolist()))
+    mg.frames_per_graph = FPG
+    return mg
 
 
 def main():
@@ -45,11 +43,13 @@ def main():
     tr = MPNTracker(graph_model=model, eval_params={'set_pruned_edges_to_inactive': True}, dataset_params=ds,
                     window_batch=16)
     res = {}
-    for name in ('batched', 'window_by_window', 'batched', 'window_by_window'):
+    for name in ('batched_rebuild', 'batched', 'window_by_window') * 2:
         tr.full_graph = full_graph(win, ds)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if name == 'batched':
+        if name == 'batched_rebuild':
+            tr._evaluate_batched_rebuild()
+        elif name == 'batched':
             tr._evaluate_batched()
         else:
             tr._evaluate_window_by_window(None)
@@ -57,12 +57,17 @@ def main():
         res[name] = (time.perf_counter() - t0, tr.full_graph.graph_obj.edge_preds)
     go = tr.full_graph.graph_obj
     nwin = T - FPG + 1
-    diff = float((res['batched'][1] - res['window_by_window'][1]).abs().max())
+    diff = max(float((res[a][1] - res['window_by_window'][1]).abs().max()) for a in ('batched', 'batched_rebuild'))
     print(f'sequence: T={T} frames, N={win.N} nodes, E_full={go.num_edges} directed candidate edges, '
           f'{nwin} windows of {FPG} frames, k={K}')
-    for name in ('batched', 'window_by_window'):
+    for name in ('batched_rebuild', 'batched', 'window_by_window'):
         print(f'  {name:17s}: {res[name][0] * 1e3:8.1f} ms  ({nwin / res[name][0]:7.1f} windows/s)')
     print(f'  max |edge_pred difference| between the schedules: {diff:.2e}')
+    for a in ('batched', 'batched_rebuild'):
+        d = (res[a][1] - res['window_by_window'][1]).abs()
+        print(f'    {a}: {int((d > 1e-3).sum())} of {d.numel()} directed edges differ by more than 1e-3 '
+              f'(near-ties at the k boundary are resolved by the last ulp of the distance, whose summation order differs '
+              f'between the edge-list and the dense kernels)')
 
 
 if __name__ == '__main__':
