@@ -323,8 +323,17 @@ class MOTMPNet(nn.Module):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
         x_ext = getattr(data, 'x_ext', None) if self.has_mask_branch else None
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('backward through the CUDA kernels is not wired yet: call under '
-                                      'torch.no_grad() (as MPNTracker does, tracker/mpn_tracker.py:122)')
+            # training (pl_module.py:122-135): the core network runs through the deterministic fp32 training kernels
+            # with a hand-written backward; loss.backward() fills p.grad of the encoder / MPNet / classifier weights
+            if x_ext is not None:
+                raise NotImplementedError('training through the attention / mask branch is not built: pass x_ext=None '
+                                          '(tracking loss of the core network) or call under torch.no_grad()')
+            if return_state:
+                raise NotImplementedError('return_state is an inference-only option')
+            from ..training import CoreTrainer
+            tr = getattr(self, '_core_trainer', None) or CoreTrainer(self)
+            logits = tr.autograd_logits(data)
+            return {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])], 'mask_predictions': []}
         layout = ops.edge_layout(edge_index, x.shape[0])
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
         # the attention branch needs the logits of EVERY step (models/mpn.py:377), the output only the last ones

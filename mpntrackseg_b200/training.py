@@ -81,6 +81,25 @@ class _Linear:
 CORE_PREFIXES = ('encoder.', 'classifier.', 'MPNet.')
 
 
+class _CoreLogits(torch.autograd.Function):
+    """forward_core / backward_core as one autograd node over the core parameters."""
+
+    @staticmethod
+    def forward(ctx, trainer, data, *params):
+        lg_slot, c = trainer.forward_core(data)
+        ctx.trainer, ctx.c = trainer, c
+        out = torch.empty_like(lg_slot)
+        out[:, c['sedge'].long()] = lg_slot                            # slot order -> the caller's edge order
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        tr, c = ctx.trainer, ctx.c
+        tr.grad.zero_()
+        tr.backward_core(c, g_out[:, c['sedge'].long()].contiguous())
+        return (None, None) + tuple(g.clone() for g in tr.g.values())
+
+
 class CoreTrainer:
     """Owns a flat parameter / gradient / Adam-state bucket for the core network of a ``MOTMPNet``."""
 
@@ -102,6 +121,7 @@ class CoreTrainer:
             self.g[n] = self.grad[off:off + k].view_as(p)
             off += k
         self.lr, self.weight_decay, self.betas, self.eps, self.t = lr, weight_decay, betas, eps, 0
+        object.__setattr__(model, '_core_trainer', self)       # one flat bucket per model: MOTMPNet.forward reuses it under autograd
 
     # ---------------------------------------------------------------- helpers
     def _lin(self, prefix, slot, relu):
@@ -119,9 +139,19 @@ class CoreTrainer:
         """Forward (models/mpn.py:349-381), loss (pl_module.py:88-105) and backward of the core network for
         one graph (or block-diagonal batch).  Gradients are ACCUMULATED into ``self.g`` (zeroed first
         unless zero_grad=False).  Returns the loss as a 1-element device tensor."""
-        m = self.model
         if zero_grad:
             self.grad.zero_()
+        lg_all, ctx = self.forward_core(data)
+        # loss (slot order on both sides) and its gradient w.r.t. the logits
+        labels = edge_labels.to(lg_all.device, torch.float32).reshape(-1)[ctx['sedge'].long()].contiguous()
+        loss, _, g_logits = ops.weighted_bce(lg_all, labels, weight=tracking_weight, want_grad=True)
+        self.backward_core(ctx, g_logits)
+        return loss
+
+    def forward_core(self, data):
+        """Forward with stored activations.  Returns (logits [num_class_steps, E] in SLOT order, ctx); ``ctx['sedge']``
+        maps a slot to the caller's edge id."""
+        m = self.model
         x = data.x
         pooled = ops.avgpool(x) if x.dim() > 2 else x.contiguous()
         n = pooled.shape[0]
@@ -184,10 +214,24 @@ class CoreTrainer:
         if steps == 0:
             raise NotImplementedError('training with num_enc_steps == 0')
 
-        # ---- loss (slot order on both sides) and its gradient w.r.t. the logits
-        labels = edge_labels.to(dev, torch.float32).reshape(-1)[sedge.long()].contiguous()
-        lg_all = torch.stack(logits)
-        loss, _, g_logits = ops.weighted_bce(lg_all, labels, weight=tracking_weight, want_grad=True)
+        ctx = dict(lay=lay, sedge=sedge, srow=srow, scol=scol, perm_c=perm_c, ptr_c=ptr_c, n=n, e=e, n_out=n_out,
+                   steps=steps, first_cls=first_cls, saved=saved, acts_n=acts_n, acts_e=acts_e, dn=dn, de=de)
+        return torch.stack(logits), ctx
+
+    def backward_core(self, ctx, g_logits):
+        """Hand-written backward from d loss / d logits ([num_class_steps, E], slot order); parameter gradients are
+        ACCUMULATED into ``self.g``."""
+        lay, srow, perm_c, ptr_c = ctx['lay'], ctx['srow'], ctx['perm_c'], ctx['ptr_c']
+        n, e, n_out, steps, first_cls, saved = ctx['n'], ctx['e'], ctx['n_out'], ctx['steps'], ctx['first_cls'], ctx['saved']
+        acts_n, acts_e, dn, de = ctx['acts_n'], ctx['acts_e'], ctx['dn'], ctx['de']
+        dev = g_logits.device
+        enc_n, enc_e = self._mlp('encoder.node_model'), self._mlp('encoder.edge_model')
+        edge_mlp = self._mlp('MPNet.edge_model.edge_model')
+        flow = {'out': self._mlp('MPNet.node_model.flow_out_model'), 'in': self._mlp('MPNet.node_model.flow_in_model')}
+        node_lin = self._lin('MPNet.node_model.node_model', 0, True)
+        cls = self._mlp('classifier.edge_model')
+        ranges = (('out', 0, n_out, dn), ('in', n_out, e, 0))
+        g_logits = g_logits.contiguous()
 
         # ---- backward through the steps
         gxs = torch.zeros((n, dn), dtype=torch.float32, device=dev)
@@ -237,7 +281,12 @@ class CoreTrainer:
         g_act = ge0
         for i in range(len(enc_e) - 1, -1, -1):
             g_act = enc_e[i].bwd(acts_e[i], acts_e[i + 1], g_act, need_gx=i > 0)
-        return loss
+
+    # ---------------------------------------------------------------- autograd bridge
+    def autograd_logits(self, data):
+        """Logits [num_class_steps, E] in the CALLER'S edge order, attached to the autograd graph of the core
+        parameters: ``loss.backward()`` (pl_module.py:126-135) runs ``backward_core`` and fills ``p.grad``."""
+        return _CoreLogits.apply(self, data, *self.named.values())
 
     # ---------------------------------------------------------------- optimizer
     def all_reduce_grads(self, group=None):

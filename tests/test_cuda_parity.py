@@ -677,6 +677,47 @@ def test_training_backward_matches_autograd_of_the_oracle(name):
     assert torch.equal(g1, tr.grad)
 
 
+def test_motmpnet_forward_under_autograd_fills_parameter_gradients():
+    """The reference's training call (pl_module.py:122-135): model(data) with autograd on, a torch loss on
+    the returned logits, loss.backward().  p.grad of the core weights must match autograd through the oracle; a torch
+    optimizer step must move the weights the kernels read."""
+    c = load_case('tiny_nonrecip')
+    win, gold, mp = c['win'], c['gold'], c['mp']
+    P = {k: v for k, v in c['P'].items() if k.startswith(('encoder.', 'classifier.', 'MPNet.'))}
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    labels = (win.ident[ei[0]] == win.ident[ei[1]]).float()
+    ref_loss, ref_g = _oracle_loss_and_grads(P, mp, win.x, ei, ea, labels, 1.0)
+    model = make_model(mp, c['P'], 'fp32').train()
+    data = Data()
+    data.x, data.edge_index, data.edge_attr, data.x_ext = win.x.to(dev()), ei.to(dev()), ea.to(dev()), None
+    opt = torch.optim.Adam([p for n, p in model.named_parameters() if n in P], lr=1e-3)
+    out = model(data)
+    assert len(out['classified_edges']) == mp['num_class_steps'] and out['classified_edges'][-1].shape == (ei.shape[1], 1)
+    with torch.no_grad():
+        ref_logits = model.eval()(data)['classified_edges']
+    model.train()
+    for a, b in zip(out['classified_edges'], ref_logits):           # same logits as the inference kernels, caller's edge order
+        assert float((a.detach() - b).abs().max()) <= 1e-3 * max(1.0, float(b.abs().max()))
+    loss = mpn_ref.weighted_bce_loss(out['classified_edges'], labels.to(dev()))
+    assert abs(float(loss) - ref_loss) <= 2e-4 * max(1.0, abs(ref_loss))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, g in ref_g.items():
+        got = named[k].grad.cpu()
+        scale = float(g.abs().max()) + 1e-12
+        assert float((got - g).abs().max()) / scale <= 2e-3, k
+    before = named['classifier.edge_model.fc_layers.2.bias'].detach().clone()
+    opt.step()
+    assert not torch.equal(before, named['classifier.edge_model.fc_layers.2.bias'].detach())
+    with torch.no_grad():
+        moved = model.eval()(data)['classified_edges'][-1]
+    assert float((moved - ref_logits[-1]).abs().max()) > 0        # the kernels read the updated weights
+    data.x_ext = torch.zeros(win.N, 256, 14, 14, device=dev())
+    with pytest.raises(NotImplementedError):
+        model.train()(data)
+
+
 def test_adam_step_matches_torch_adam():
     from mpntrackseg_b200.training import CoreTrainer
     c = load_case('tiny_nonrecip')
