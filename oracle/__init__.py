@@ -13,6 +13,9 @@ CPU), the algorithms of
 * ``src/mot_neural_solver/data/mot_graph.py:195-221,283-316`` (edge construction / graph assembly)
 * ``src/mot_neural_solver/models/mpn.py:33-394`` + ``models/mlp.py:4-28`` + ``models/cnn.py:4-84``
 * ``src/mot_neural_solver/tracker/mpn_tracker.py:96-141``  (prune -> forward -> sigmoid -> scatter back)
+* ``src/mot_neural_solver/tracker/mpn_tracker.py:143-210`` + ``utils/graph.py:165-207`` (sliding windows over a
+  sequence, per-edge averaging, undirected merge, pruning at 0.5; ``tracker_ref.py``)
+* ``src/mot_neural_solver/data/mot_graph.py:223-262``      (edge labels of the network-flow formulation)
 * ``src/mot_neural_solver/pl_module/pl_module.py:88-120``  (weighted BCE loss)
 
 and of the third-party ``torch-scatter==2.0.4`` calls made on that path
