@@ -274,17 +274,26 @@ int mpn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   void* stream);
 
-/* Same contract as mpn_mp_forward (num_steps >= 1), evaluated on the tcgen05 tensor cores:
+/* Same contract as mpn_mp_forward (1 <= num_steps <= 1000), evaluated on the tcgen05 tensor cores:
  * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).
- * *status (device int32) is set non-zero if any activation left the fp16 range (> 65504); the
- * outputs are then invalid and the caller must rerun with mpn_mp_forward (fp32 kernels).
+ * Range: step t runs on operands scaled by 2^-s_t, s_t chosen on the device from the previous step's largest
+ * activation and the growth of the node state (exact power-of-two scaling of a piecewise-linear network;
+ * s_t = 0 while values stay below ~1e3), so node states far beyond the fp16 range stay on this path.
+ * *status (device int32) is set non-zero only if a value still left the fp16 range (one-step growth beyond the
+ * 64x headroom); the outputs are then invalid and the caller must rerun with mpn_mp_forward (fp32 kernels).
  * workspace bytes: mpn_mp_tc_workspace(N, E). */
 int64_t mpn_mp_tc_workspace(int64_t num_nodes, int64_t num_edges);
 int mpn_mp_forward_tc(const mpn_core_weights* h_w, const mpn_edge_layout* h_g, const float* x_init,
                       const float* e_init, int32_t num_steps, int32_t first_class_step,
                       void* workspace, float* logits, float* x_out, float* e_out, int32_t* status,
                       void* stream);
+
+/* Diagnostics of the last mpn_mp_forward_tc run on `workspace` (same n, e): the scale exponents s_t and the maxima
+ * they were derived from, entries [0, num_steps + 2) indexed by step (1-based).  h_* are HOST arrays and may be
+ * NULL.  SYNCS. */
+int mpn_mp_tc_read_schedule(const void* workspace, int64_t num_nodes, int64_t num_edges, int32_t num_steps,
+                            int32_t* h_sched, float* h_amax, float* h_xmax, void* stream);
 
 #ifdef __cplusplus
 }

@@ -342,10 +342,10 @@ int mpn_edge_feats_assemble(const int64_t* row, const int64_t* col, int64_t np, 
                             const float* h, const float* w, const float* fx, const float* fy,
                             float fps, const float* rd, int64_t ad, float* attr, int64_t* eidx,
                             void* stream) {
-  MPN_CHECK_ARG(np >= 0, "edge_feats_assemble: bad size");
+  MPN_CHECK_ARG(np >= 0 && (ad == 5 || ad == 6), "edge_feats_assemble: bad size");
+  if (np == 0) return MPN_OK;                  // an empty tensor has a null data pointer
   MPN_CHECK_ARG((rd != nullptr && ad == 6) || (rd == nullptr && ad == 5),
                 "edge_feats_assemble: attr_dim must be 6 with reid_dist, 5 without (got %lld)", (long long)ad);
-  if (np == 0) return MPN_OK;
   MPN_CHECK_ARG(row && col && frame && h && w && fx && fy && attr && eidx, "edge_feats_assemble: null pointer");
   edge_feats_kernel<<<grid_for(np, 256), 256, 0, as_stream(stream)>>>(row, col, np, frame, h, w, fx, fy,
                                                                     fps, rd, ad, attr, eidx); count_launch();

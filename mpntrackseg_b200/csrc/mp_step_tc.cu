@@ -4,8 +4,9 @@
 // The four dense layers of a step (edge MLP 160->80->16, flow MLP 80->56->32) run as
 // tcgen05.mma kind::f16 with the ACTIVATIONS in TMEM (A operand, written by the epilogue
 // threads with tcgen05.st) and the WEIGHTS resident in shared memory (B operand, K-major).
-// Precision: every operand is split v ~= hi + lo in fp16 (22 significant bits) and each K step
-// issues hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM -- single-pass bf16/tf32 breaks
+// Precision: every operand is split v ~= hi + lo in fp16 (22 significant bits; the low part is stored lifted by
+// 2^10 so that it stays a normal number, tc_ptx.cuh "lifted low part") and each layer issues lo*hi + hi*lo for
+// all K steps, folds them in with the accumulator input scale 2^-10, then hi*hi, with fp32 accumulation in TMEM -- single-pass bf16/tf32 breaks
 // the 1e-3 parity bar after 12 recurrent steps, bf16 hi/lo is 10-20x less accurate than fp16
 // hi/lo (tools/emulate_split_bf16.py).  fp16 range overflow (> 65504) is detected and reported
 // through `status`; the caller then reruns on the fp32 kernels (mp_step.cu).
@@ -33,13 +34,10 @@
 namespace mpn {
 namespace tc {
 
-int variant();   // 2: two tiles in flight, operands staged through TMEM; 3 (default): three tiles, SS-mode layer-1 operands
-
 using namespace ptx;
 
 constexpr int TS = 128;
 constexpr int DN = 32, DE = 16, EH = 80, FH = 56, FHP = 64, CH = 8;
-constexpr int NTHREADS = 512;
 
 // ---- shared-memory weight image (bytes). Slab = one K=16 step of a B operand: [n/8][k/8][n%8][8 halfs]
 constexpr int L1_KS = 6, L1_SLAB = EH * 32;
@@ -54,28 +52,6 @@ constexpr int OFF_F32 = OFF_L4L + L4_KS * L4_SLAB;          // fp32 tail
 constexpr int F_B1 = 0, F_FB0 = F_B1 + DE, F_FB1 = F_FB0 + FHP, F_CW0 = F_FB1 + DN, F_CB0 = F_CW0 + DE * CH,
               F_CW1 = F_CB0 + CH, F_CB1 = F_CW1 + CH, F_COUNT = F_CB1 + 4;
 constexpr int IMG_BYTES = (OFF_F32 + F_COUNT * 4 + 127) / 128 * 128;
-
-// ---- TMEM column map inside a group's 256 columns.  Each epilogue rewrites an accumulator chunk of
-//      16 fp32 columns IN PLACE as the next layer's operand: [hi: 8 cols of fp16 pairs | lo: 8 cols].
-constexpr int C_XCH = 0, C_XCL = 32;        // x[col] hi / lo            (K = 64)
-constexpr int C_EH = 64, C_EL = 80;         // [e_init | e] hi / lo      (K = 32)
-constexpr int C_D1 = 96, C_A2 = C_D1;       // layer-1 accumulator (80 cols) -> layer-2 operand (K = 80)
-constexpr int C_D2 = 64, C_A3 = 80;         // layer-2 accumulator (16 cols) and e' operand (16 cols), over the dead E region
-constexpr int C_D3 = 176, C_A4 = C_D3;      // layer-3 accumulator (64 cols) -> layer-4 operand (K = 64)
-constexpr int C_D4 = 0;                     // layer-4 accumulator, 32 cols (over the dead x[col])
-
-// ---- per-row sums are made per warp over its 32 consecutive slots ("chunk"); rows that cross a
-//      chunk boundary leave partial sums that the node kernel adds up in chunk order.
-constexpr int CHUNK = 32;
-
-// ---- dynamic shared memory map
-constexpr int MSG_LD = DN + 1;
-constexpr int STAGE_ROW = 400;                                      // 24 x 16 B operands per edge + 16 B pad (bank spread)
-constexpr int SM_MSG = IMG_BYTES;                                   // float [8 warps][32*MSG_LD]
-constexpr int SM_STAGE = SM_MSG + 8 * CHUNK * MSG_LD * 4;           // [2 groups][TS][STAGE_ROW]  next tile's operands
-constexpr int SM_BAR = SM_STAGE + 2 * TS * STAGE_ROW;               // u64 d_ready[2] (+2 spare)
-constexpr int SM_TMEM = SM_BAR + 4 * 8;
-constexpr int SMEM_BYTES = SM_TMEM + 16;
 
 __device__ __forceinline__ int slab_off(int n, int k16) {           // byte offset inside a slab
   return (n >> 3) * 256 + (k16 >> 3) * 128 + (n & 7) * 16 + (k16 & 7) * 2;
@@ -93,7 +69,7 @@ __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ im
     const float* fb1 = dir == 0 ? w.fout_b1 : w.fin_b1;
     auto put = [&](int off_h, int off_l, int slab_bytes, int n, int k, float v) {
       const __half h = __float2half_rn(v);
-      const __half l = __float2half_rn(v - __half2float(h));
+      const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
       const int o = (k >> 4) * slab_bytes + slab_off(n, k & 15);
       *reinterpret_cast<__half*>(img + off_h + o) = h;
       *reinterpret_cast<__half*>(img + off_l + o) = l;
@@ -134,10 +110,32 @@ __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ im
   }
 }
 
+// =================================================================== range bookkeeping
+// Per forward: sched[t] = s_t (exponent of the step's scale), amax[t] = float bits of the largest true activation
+// the edge kernel of step t saw, xmax[t] = largest |x_lat| consumed by step t (t = 1..num_steps; all zeroed at start).
+constexpr int MAX_STEPS = 1000;
+constexpr float SCALE_TARGET = 1024.f;      // lagged maximum is brought to <= 2^10: 64x headroom to the fp16 range
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }   // 2^e, |e| <= 126
+// s_{t+1} from what is known when the node kernel of step t starts: the edge kernel's activation maximum of step t
+// and the node-state maxima of steps t and t-1 (their ratio predicts the growth of the state being produced).
+__device__ __forceinline__ int scale_for(float a_t, float x_t, float x_tm1) {
+  float growth = x_tm1 > 0.f ? x_t / x_tm1 : 4.f;
+  growth = fminf(fmaxf(growth, 1.f), 64.f);
+  const float lag = fmaxf(a_t, x_t * growth);
+  if (!(lag > SCALE_TARGET)) return 0;
+  int e;
+  frexpf(lag / SCALE_TARGET, &e);             // lag / target = m * 2^e, m in [0.5, 1)
+  return e > 100 ? 100 : e;
+}
+__device__ __forceinline__ void atomic_max_f32(uint32_t* addr, float v) {   // v >= 0: integer order = float order
+  const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(addr, m);
+}
+
 // =================================================================== node-side kernels
 __device__ __forceinline__ void store_split_row(__half* __restrict__ row64, int lane, float v, int* ovf) {
   const __half h = __float2half_rn(v);
-  const __half l = __float2half_rn(v - __half2float(h));
+  const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
   row64[lane] = h;
   row64[32 + lane] = l;
   if (!(fabsf(v) < 65000.f)) *ovf = 1;
@@ -149,7 +147,7 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
                                                          const float* __restrict__ w0, const float* __restrict__ b0,
                                                          __half* __restrict__ xi, __half* __restrict__ xl0,
                                                          float* __restrict__ pinit, float* __restrict__ prow,
-                                                         int32_t* __restrict__ status) {
+                                                         uint32_t* __restrict__ xmax, int32_t* __restrict__ status) {
   __shared__ float s_w[64 * EH];     // [i][o], i over W0 columns 0..63
   __shared__ float s_b[EH];
   for (int idx = threadIdx.x; idx < 64 * EH; idx += blockDim.x) {        // coalesced along a weight row
@@ -162,8 +160,10 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   int ovf = 0;
+  float mx = 0.f;
   for (int64_t r = warp; r < n; r += nwarps) {
     const float v = x_init[r * DN + lane];
+    mx = fmaxf(mx, fabsf(v));
     store_split_row(xi + r * 64, lane, v, &ovf);
     store_split_row(xl0 + r * 64, lane, v, &ovf);
     float a0[3], a1[3];
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
       if (o < EH) { pinit[r * EH + o] = a0[q]; prow[r * EH + o] = a0[q] + a1[q]; }
     }
   }
+  atomic_max_f32(xmax + 1, mx);                                         // the state consumed by step 1 (scale s_1 = 0)
   if (ovf) atomicOr(status, 1);
 }
 
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
                                                          const float* __restrict__ node_w, const float* __restrict__ node_b,
                                                          const float* __restrict__ w0, const float* __restrict__ pinit,
                                                          __half* __restrict__ xl_next, float* __restrict__ prow,
-                                                         float* __restrict__ x_out, int32_t* __restrict__ status) {
+                                                         float* __restrict__ x_out, int32_t step, int32_t* __restrict__ sched,
+                                                         const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax,
+                                                         int32_t* __restrict__ status) {
   // Warp per node, lane = output feature.  The lane's column of the node Linear lives in REGISTERS (64 values); a
   // node's input vector is staged in a per-warp shared-memory buffer and read back as 16-byte broadcasts, so a node
   // costs ~120 shared-memory instructions instead of 96 shuffles + 160 loads.  The next node's inputs are loaded while the
@@ -224,6 +227,12 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
   const float bn = s_bn[lane];
   float* vec = s_vec[threadIdx.x >> 5];
   int ovf = 0;
+  // scale of the step that will consume this kernel's outputs (x_lat rows and prow are written pre-scaled)
+  const int s_next = scale_for(__uint_as_float(amax[step]), __uint_as_float(xmax[step]),
+                               step > 1 ? __uint_as_float(xmax[step - 1]) : 0.f);
+  const float sig_next = pow2i(-s_next);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sched[step + 1] = s_next;
+  float mx = 0.f;
 
   auto load_ptrs = [&](int64_t r, int32_t* p) { p[0] = in_ptr[r]; p[1] = in_ptr[r + 1]; p[2] = out_ptr[r]; p[3] = out_ptr[r + 1]; };
   // one direction's flow vector: the row sum written by the edge kernel, or its partials combined in fixed order
@@ -291,7 +300,8 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
     vec[2 * DN + lane] = xn;
     __syncwarp();
     if (x_out != nullptr) x_out[r * DN + lane] = xn;
-    store_split_row(xl_next + r * 64, lane, xn, &ovf);
+    mx = fmaxf(mx, xn);
+    store_split_row(xl_next + r * 64, lane, xn * sig_next, &ovf);
     float a[3] = {pin[0], pin[1], pin[2]};
 #pragma unroll
     for (int i = 0; i < DN / 4; ++i) {
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int o = lane + 32 * q;
-      if (o < EH) prow[r * EH + o] = a[q];
+      if (o < EH) prow[r * EH + o] = a[q] * sig_next;
     }
     __syncwarp();                                                       // vec is rewritten by the next node
     fl[0] = nfl[0]; fl[1] = nfl[1];
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
 #pragma unroll
     for (int q = 0; q < 4; ++q) pn[q] = p2[q];
   }
+  atomic_max_f32(xmax + step + 1, mx);
   if (ovf) atomicOr(status, 1);
 }
 
@@ -330,8 +341,8 @@ __global__ void split_edges_kernel(const float* __restrict__ e, int64_t num_edge
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 v = __ldg(p + q);
-      split2(v.x, v.y, hi[2 * q], lo[2 * q]);
-      split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+      split2s(v.x, v.y, hi[2 * q], lo[2 * q]);
+      split2s(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
       if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) < 65000.f)) ovf = 1;
     }
     out[s * 4 + 0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -343,7 +354,9 @@ __global__ void split_edges_kernel(const float* __restrict__ e, int64_t num_edge
 }
 
 // split rows -> fp32 (final edge state for callers that ask for it)
-__global__ void unsplit_edges_kernel(const uint4* __restrict__ in, int64_t num_edges, float* __restrict__ e) {
+__global__ void unsplit_edges_kernel(const uint4* __restrict__ in, int64_t num_edges, float* __restrict__ e,
+                                     const int32_t* __restrict__ sched, int32_t last_step) {
+  const float inv = pow2i(sched[last_step]);                             // the state is stored in the last step's scale
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_edges; s += (int64_t)gridDim.x * blockDim.x) {
     const uint4 h0 = in[s * 4], h1 = in[s * 4 + 1], l0 = in[s * 4 + 2], l1 = in[s * 4 + 3];
     const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -352,8 +365,8 @@ __global__ void unsplit_edges_kernel(const uint4* __restrict__ in, int64_t num_e
     for (int j = 0; j < 8; ++j) {
       const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
       const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
-      e[s * DE + 2 * j] = a.x + b.x;
-      e[s * DE + 2 * j + 1] = a.y + b.y;
+      e[s * DE + 2 * j] = fmaf(b.x, 1.f / LO_SCALE, a.x) * inv;
+      e[s * DE + 2 * j + 1] = fmaf(b.y, 1.f / LO_SCALE, a.y) * inv;
     }
   }
 }
@@ -373,7 +386,9 @@ struct TcArgs {
   float* flow; float* part; float* logits;
   const uint8_t* wimg_out; const uint8_t* wimg_in;
   int32_t* status;
-  long long* trace;      // optional [16 stamps x 64 tiles] cycle trace of CTA 0 / group 0 (development)
+  int32_t step;              // 1-based step index
+  const int32_t* sched;      // sched[t] = s_t, see "range bookkeeping"
+  uint32_t* amax;            // amax[step] receives the largest true activation of this launch
 };
 
 __device__ __forceinline__ void ld_f32x16(float (&d)[16], const float* __restrict__ p) {
@@ -398,389 +413,9 @@ __device__ __forceinline__ void relu_split16(const uint32_t (&acc)[16], const fl
   for (int j = 0; j < 8; ++j) {
     const float a = fmaxf(__uint_as_float(acc[2 * j]) + add[2 * j], 0.f);
     const float b = fmaxf(__uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], 0.f);
-    split2(a, b, hi[j], lo[j]);
+    split2s(a, b, hi[j], lo[j]);
     ovf |= hi[j] + 0x04000400u;        // fp16 inf (0x7C00) + 0x0400 sets the half's top bit
   }
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1) mp_edge_tc_kernel(TcArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
-
-  // CTAs [0, n_out_ctas) walk flow_out tiles, the rest walk flow_in tiles.
-  const int total_tiles = a.tiles_out + a.tiles_in;
-  int n_out_ctas = (int)(((int64_t)gridDim.x * a.tiles_out + total_tiles - 1) / total_tiles);
-  if (a.tiles_out > 0 && n_out_ctas == 0) n_out_ctas = 1;
-  if (a.tiles_in > 0 && n_out_ctas >= (int)gridDim.x) n_out_ctas = gridDim.x - 1;
-  if (a.tiles_in == 0) n_out_ctas = gridDim.x;
-  const bool dir_out = (int)blockIdx.x < n_out_ctas;
-  const int cta_in_dir = dir_out ? blockIdx.x : blockIdx.x - n_out_ctas;
-  const int ctas_in_dir = dir_out ? n_out_ctas : gridDim.x - n_out_ctas;
-  const int tiles_dir = dir_out ? a.tiles_out : a.tiles_in;
-  const int64_t seg_base = dir_out ? 0 : a.num_out;
-  const int64_t seg_end = dir_out ? a.num_out : a.num_edges;
-
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);       // d_ready[group]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
-  }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
-  const float* s_f = reinterpret_cast<const float*>(smem + OFF_F32);
-
-  // Two groups of 8 warps, one 128-edge tile in flight each; a group owns 256 TMEM columns.  Every
-  // edge (TMEM lane) is served by TWO threads: half A (warps 0-3 of the group) and half B (warps 4-7)
-  // split the columns of each epilogue, the operand loads and the bookkeeping.
-  const int g = warp >> 3;
-  const bool half_b = ((warp >> 2) & 1) != 0;
-  const int wq = warp & 3;                                            // quarter of the tile = this warp's TMEM lanes
-  const int gt = wq * 32 + lane;                                      // edge row inside the tile
-  const uint32_t tcol = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u;   // uniform: MMA operand base
-  const uint32_t tlane = tcol + ((uint32_t)(wq * 32) << 16);
-  float* s_msg = reinterpret_cast<float*>(smem + SM_MSG) + (g * 4 + wq) * CHUNK * MSG_LD;
-  const uint32_t stage_warp = smem_u32(smem + SM_STAGE + (g * TS + wq * CHUNK) * STAGE_ROW);
-  const uint4* s_stage = reinterpret_cast<const uint4*>(smem + SM_STAGE + (g * TS + gt) * STAGE_ROW);
-  uint64_t* d_ready = &bars[g];
-  const int64_t chunk_off = dir_out ? 0 : a.chunks_out;
-  const int dir_off = dir_out ? DN : 0;                               // cat(flow_in, flow_out), mpn.py:97
-  uint32_t pd = 0;
-  __half2 vmax = __floats2half2_rn(0.f, 0.f);                         // running max of every hi word (overflow check)
-
-  // ---- MMA issue: run by the group's first warp (all lanes, uniform operands), one elected lane issues.
-  const uint64_t dbase = smem_desc_kmajor(smem_u32(smem), 128, 256);   // + (byte offset >> 4) per slab
-  auto step3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
-    const uint64_t dh = dbase + (uint64_t)(off_h >> 4), dl = dbase + (uint64_t)(off_l >> 4);
-    mma_ts(d, ah, dh, idesc, first ? 0u : 1u);
-    mma_ts(d, ah, dl, idesc, 1u);
-    mma_ts(d, al, dh, idesc, 1u);
-  };
-  auto issue_layer = [&](int layer) {
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t cb = tcol;
-      if (layer == 1) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          step3(cb + C_D1, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB,
-                idesc_f16(128, EH), ks == 0);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          step3(cb + C_D1, cb + C_EH + 8 * ks, cb + C_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB,
-                OFF_L1L + (4 + ks) * L1_SLAB, idesc_f16(128, EH), false);
-      } else if (layer == 2) {
-#pragma unroll
-        for (int ks = 0; ks < L2_KS; ++ks)
-          step3(cb + C_D2, cb + C_A2 + 16 * ks, cb + C_A2 + 16 * ks + 8, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
-                idesc_f16(128, DE), ks == 0);
-      } else if (layer == 3) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          step3(cb + C_D3, cb + C_XCH + 8 * ks, cb + C_XCL + 8 * ks, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB,
-                idesc_f16(128, FHP), ks == 0);
-        step3(cb + C_D3, cb + C_A3, cb + C_A3 + 8, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, idesc_f16(128, FHP),
-              false);
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < L4_KS; ++ks)
-          step3(cb + C_D4, cb + C_A4 + 16 * ks, cb + C_A4 + 16 * ks + 8, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
-                idesc_f16(128, DN), ks == 0);
-      }
-      mma_commit(d_ready);
-    }
-    __syncwarp();
-  };
-  // operands written to TMEM by all 256 threads of the group -> visible to the MMAs of `layer`
-  auto publish_and_issue = [&](int layer) {
-    tc_wait_st();
-    tc_fence_before();
-    named_barrier(1 + g, 2 * TS);
-    if (!half_b && wq == 0) issue_layer(layer);
-  };
-  // one accumulator chunk (16 fp32 columns) -> + add -> ReLU -> fp16 hi/lo, written back in place
-  auto epilogue_chunk = [&](int col, const float* add) {
-    uint32_t acc[16];
-    tmem_ld16(tlane + col, acc);
-    tc_wait_ld();
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
-      vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
-    }
-    tmem_st8(tlane + col, hi);
-    tmem_st8(tlane + col + 8, lo);
-  };
-
-  // Operand rows of the warp's 32 edges -> staging rows (x_init[c] 128 B at +0, x_lat[c] 128 B at +128,
-  // e_init 64 B at +256, e 64 B at +320).  Lanes cooperate so that every request covers whole 128-B
-  // lines.  Half A fetches (and later stores to TMEM) the node rows, half B the edge rows.
-  auto prefetch_nodes = [&](int32_t c) {
-    const int sub8 = lane >> 3, pc8 = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = i * 4 + sub8;
-      const int32_t cr = __shfl_sync(0xffffffffu, c, row);
-      cp_async16(stage_warp + row * STAGE_ROW + pc8 * 16, a.xi + (int64_t)cr * 8 + pc8);
-      cp_async16(stage_warp + row * STAGE_ROW + 128 + pc8 * 16, a.xl + (int64_t)cr * 8 + pc8);
-    }
-  };
-  auto prefetch_edges = [&](int64_t chunk_slot0, int64_t last_slot) {
-    const int sub4 = lane >> 2, pc4 = lane & 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = i * 8 + sub4;
-      int64_t sl = chunk_slot0 + row;
-      sl = sl < last_slot ? sl : last_slot;                            // clamp: loads stay in range
-      cp_async16(stage_warp + row * STAGE_ROW + 256 + pc4 * 16, a.ei + sl * 4 + pc4);
-      cp_async16(stage_warp + row * STAGE_ROW + 320 + pc4 * 16, a.es_in + sl * 4 + pc4);
-    }
-  };
-
-  // Per-tile indices are loaded two tiles ahead so that no load latency sits on the tile's chain.
-  struct TileIdx { int64_t base; int cnt; int32_t r, x, nb; bool have; };   // x: col (half A) / slot_edge (half B)
-  auto load_idx = [&](int p) {
-    TileIdx t;
-    t.have = 2 * p + g < tiles_dir;
-    t.base = 0; t.cnt = 0; t.r = 0; t.x = 0; t.nb = -1;
-    if (t.have) {
-      t.base = seg_base + (int64_t)(2 * p + g) * TS;
-      t.cnt = (int)(seg_end - t.base < TS ? seg_end - t.base : TS);
-      const int64_t slot = gt < t.cnt ? t.base + gt : t.base + t.cnt - 1;   // clamp: loads stay in range
-      t.r = a.slot_row[slot];
-      if (!half_b) {
-        t.x = a.slot_col[slot];
-      } else {
-        if (a.logits != nullptr) t.x = a.slot_edge[slot];
-        // rows adjacent to this warp's chunk (lane 0: slot before, lane 31: slot after), for the row sums
-        const int64_t cs = t.base + wq * CHUNK;
-        const int cw = t.cnt - wq * CHUNK;
-        // one predicated load (lane 0: the slot before the chunk, lane 31: the slot after it)
-        const bool want = (lane == 0 && cw > 0 && cs > seg_base) || (lane == 31 && cw >= CHUNK && cs + CHUNK < seg_end);
-        if (want) t.nb = a.slot_row[lane == 0 ? cs - 1 : cs + CHUNK];
-      }
-    }
-    return t;
-  };
-  // Row sums of one tile's messages (in s_msg), this warp's 32 slots, in slot order (half B).
-  auto row_sums = [&](const TileIdx& t) {
-    const int64_t cs = t.base + wq * CHUNK;
-    int cw = t.cnt - wq * CHUNK;
-    cw = cw < 0 ? 0 : (cw > CHUNK ? CHUNK : cw);
-    if (cw > 0) {                                                     // warp-uniform
-      const int f = lane;                                             // lane = feature from here on
-      const int64_t chunk_id = chunk_off + (cs - seg_base) / CHUNK;
-      const int32_t r_prev = __shfl_sync(0xffffffffu, t.nb, 0);
-      const int32_t r_next = __shfl_sync(0xffffffffu, t.nb, 31);
-      const int32_t r_after = __shfl_down_sync(0xffffffffu, t.r, 1);
-      const bool seg_end_here = lane < cw && (lane == cw - 1 || r_after != t.r);
-      const unsigned ends = __ballot_sync(0xffffffffu, seg_end_here); // bit q: slot q closes a row segment
-      float mv[CHUNK];
-#pragma unroll
-      for (int q = 0; q < CHUNK; ++q) mv[q] = s_msg[q * MSG_LD + f];
-      float sum = 0.f;
-      bool first_seg = true;
-#pragma unroll
-      for (int q = 0; q < CHUNK; ++q) {
-        sum += mv[q];
-        if ((ends >> q) & 1u) {                                       // warp-uniform
-          const int32_t cur = __shfl_sync(0xffffffffu, t.r, q);
-          const bool starts_before = first_seg && r_prev == cur;
-          const bool continues = q == cw - 1 && r_next == cur;
-          if (!starts_before && !continues) a.flow[(int64_t)cur * 2 * DN + dir_off + f] = sum;
-          else a.part[(chunk_id * 2 + (first_seg ? 0 : 1)) * DN + f] = sum;
-          sum = 0.f;
-          first_seg = false;
-        }
-      }
-    }
-    __syncwarp();
-  };
-
-  TileIdx cur = load_idx(cta_in_dir);
-  TileIdx nxt = load_idx(cta_in_dir + ctas_in_dir);
-  TileIdx prev;
-  prev.have = false; prev.base = 0; prev.cnt = 0; prev.r = 0; prev.x = 0; prev.nb = -1;
-  if (cur.have) {
-    if (!half_b) prefetch_nodes(cur.x);
-    else prefetch_edges(cur.base + wq * CHUNK, cur.base + cur.cnt - 1);
-  }
-  int p = cta_in_dir;
-  int trace_i = 0;
-#define TC_STAMP(k) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && trace_i < 64) a.trace[trace_i * 16 + (k)] = clock64(); } while (0)
-  while (cur.have) {
-    const bool valid = gt < cur.cnt;
-    TC_STAMP(0);
-    // hoisted row term of epilogue 1, this half's columns (A: 0..47, B: 48..79); consumed after layer 1
-    float pr[48];
-    {
-      const float4* prp = reinterpret_cast<const float4*>(a.prow + (int64_t)cur.r * EH) + (half_b ? 12 : 0);
-#pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        if (half_b && j >= 8) break;
-        const float4 v = __ldg(prp + j);
-        pr[4 * j] = v.x; pr[4 * j + 1] = v.y; pr[4 * j + 2] = v.z; pr[4 * j + 3] = v.w;
-      }
-    }
-    // ---- load phase: staged operands -> TMEM (A: node rows, B: edge rows), then layer 1
-    cp_async_wait_all();
-    __syncwarp();                                                     // rows were fetched by other lanes of this warp
-    TC_STAMP(1);
-    {
-      auto st2 = [&](int col, int j) {
-        const uint4 x = s_stage[j], y = s_stage[j + 1];
-        const uint32_t w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-        tmem_st8(tlane + col, w8);
-      };
-      if (!half_b) {
-        st2(C_XCH + 0, 0);   st2(C_XCH + 8, 2);      // x_init hi
-        st2(C_XCL + 0, 4);   st2(C_XCL + 8, 6);      // x_init lo
-        st2(C_XCH + 16, 8);  st2(C_XCH + 24, 10);    // x_lat hi
-        st2(C_XCL + 16, 12); st2(C_XCL + 24, 14);    // x_lat lo
-      } else {
-        st2(C_EH + 0, 16);   st2(C_EL + 0, 18);      // e_init hi / lo
-        st2(C_EH + 8, 20);   st2(C_EL + 8, 22);      // e hi / lo
-      }
-    }
-    publish_and_issue(1);
-    TC_STAMP(2);
-    // ---- while layer 1 runs: operands of the next tile, indices of the one after, row sums of the previous
-    if (nxt.have) {
-      if (!half_b) prefetch_nodes(nxt.x);
-      else prefetch_edges(nxt.base + wq * CHUNK, nxt.base + nxt.cnt - 1);
-    }
-    p += ctas_in_dir;
-    TileIdx nn = load_idx(p + ctas_in_dir);
-    if (half_b && prev.have) row_sums(prev);
-    TC_STAMP(3);
-
-    // ---- epilogue 1: h = ReLU(D1 + prow[r]) -> layer-2 operand (A: chunks 0-2, B: chunks 3-4)
-    mbar_wait(d_ready, pd); pd ^= 1;
-    TC_STAMP(4);
-    tc_fence_after();
-    if (!half_b) {
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) epilogue_chunk(C_D1 + 16 * ch, pr + 16 * ch);
-    } else {
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) epilogue_chunk(C_D1 + 48 + 16 * ch, pr + 16 * ch);
-    }
-    publish_and_issue(2);
-    TC_STAMP(5);
-
-    // ---- epilogue 2: e' = ReLU(D2 + b1). A: state + layer-3 operand; B: classifier
-    mbar_wait(d_ready, pd); pd ^= 1;
-    TC_STAMP(6);
-    tc_fence_after();
-    {
-      uint32_t acc[16];
-      tmem_ld16(tlane + C_D2, acc);
-      float add[16];
-      ld_f32x16(add, s_f + F_B1);
-      tc_wait_ld();
-      if (!half_b) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
-          vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
-        }
-        tmem_st8(tlane + C_A3, hi);
-        tmem_st8(tlane + C_A3 + 8, lo);
-        publish_and_issue(3);
-        TC_STAMP(7);
-        if (valid) {
-          uint4* dst = a.es_out + (cur.base + gt) * 4;
-          dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          dst[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          dst[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        }
-      } else {
-        // B only reads D2 (A writes the e' operand to its own columns); it still takes part in the group
-        // barrier that precedes layer 3.
-        publish_and_issue(3);
-        if (valid && a.logits != nullptr) {                            // classifier 16 -> 8 -> 1 (fp32)
-          float hc[CH], wv[CH];
-          ld_f32x8(hc, s_f + F_CB0);
-#pragma unroll
-          for (int i = 0; i < DE; ++i) {
-            const float ei = fmaxf(__uint_as_float(acc[i]) + add[i], 0.f);
-            ld_f32x8(wv, s_f + F_CW0 + i * CH);
-#pragma unroll
-            for (int o = 0; o < CH; ++o) hc[o] = fmaf(ei, wv[o], hc[o]);
-          }
-          ld_f32x8(wv, s_f + F_CW1);
-          float lg = s_f[F_CB1];
-#pragma unroll
-          for (int o = 0; o < CH; ++o) lg = fmaf(fmaxf(hc[o], 0.f), wv[o], lg);
-          a.logits[cur.x] = lg;
-        }
-      }
-    }
-    // ---- epilogue 3: g = ReLU(D3 + fb0) -> layer-4 operand (A: chunks 0-1, B: chunks 2-3)
-    TC_STAMP(8);
-    mbar_wait(d_ready, pd); pd ^= 1;
-    TC_STAMP(9);
-    tc_fence_after();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int ch = (half_b ? 2 : 0) + q;
-      float add[16];
-      ld_f32x16(add, s_f + F_FB0 + 16 * ch);
-      epilogue_chunk(C_D3 + 16 * ch, add);
-    }
-    publish_and_issue(4);
-    TC_STAMP(10);
-
-    // ---- epilogue 4: m = ReLU(D4 + fb1) -> shared memory (A: features 0-15, B: 16-31); the row sums
-    //      run under the next tile's layer 1
-    mbar_wait(d_ready, pd); pd ^= 1;
-    TC_STAMP(11);
-    tc_fence_after();
-    {
-      const int ch = half_b ? 1 : 0;
-      uint32_t acc[16];
-      tmem_ld16(tlane + C_D4 + 16 * ch, acc);
-      float add[16];
-      ld_f32x16(add, s_f + F_FB1 + 16 * ch);
-      tc_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
-        s_msg[lane * MSG_LD + 16 * ch + j] = valid ? m : 0.f;
-      }
-    }
-    tc_fence_before();
-    TC_STAMP(12);
-    ++trace_i;
-    prev = cur; cur = nxt; nxt = nn;
-  }
-  if (prev.have) {                                                    // row sums of the group's last tile
-    named_barrier(1 + g, 2 * TS);
-    if (half_b) row_sums(prev);
-  }
-  {
-    // hi parts are truncated (rz), so a value beyond the fp16 range shows up as the largest finite
-    // fp16 (0x7BFF = 65504) or inf: flag both (conservative).
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(&vmax);
-    if ((w & 0x7FFFu) >= 0x7BFFu || ((w >> 16) & 0x7FFFu) >= 0x7BFFu) atomicOr(a.status, 1);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
 // =================================================================== variant 3: three tiles in flight
@@ -826,10 +461,43 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM3_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM3_TMEM);
+  // this step's scale (uniform): operands are true values x sigma
+  const int s_cur = a.sched[a.step];
+  const int s_prev = a.step > 1 ? a.sched[a.step - 1] : 0;
+  const float sigma = pow2i(-s_cur), inv_sigma = pow2i(s_cur);
   {
     const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) dst[i] = __ldg(src + i);
+    if (s_cur == 0) {
+      for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) dst[i] = __ldg(src + i);
+    } else {
+      // the slabs that multiply the constant (unscaled) x_init / e_init rows carry sigma themselves, and so do the
+      // biases; the classifier's output layer undoes it (all powers of two: exact up to fp16 subnormal rounding)
+      const __half2 sg = __float2half2_rn(sigma);
+      for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) {
+        uint4 v = __ldg(src + i);
+        const int o = i * 16;
+        if (o < OFF_F32) {
+          bool init_slab = false;
+          if (o < OFF_L2H) { const int ks = (o % (L1_KS * L1_SLAB)) / L1_SLAB; init_slab = ks <= 1 || ks == 4; }
+          else if (o >= OFF_L3H && o < OFF_L4H) { const int ks = ((o - OFF_L3H) % (L3_KS * L3_SLAB)) / L3_SLAB; init_slab = ks <= 1; }
+          if (init_slab) {
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], sg);
+          }
+        } else {
+          float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int fi = (o - OFF_F32) / 4 + q;
+            if (fi < F_CW0 || (fi >= F_CB0 && fi < F_CW1)) f[q] *= sigma;            // b1, fb0, fb1, cb0
+            else if (fi >= F_CW1 && fi < F_CB1) f[q] *= inv_sigma;                   // cw1
+          }
+        }
+        dst[i] = v;
+      }
+    }
   }
   if (tid == 0) {
     for (int i = 0; i < NG3; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[NG3 + i], 4); }
@@ -868,51 +536,70 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
   const uint64_t dzero = smem_desc_kmajor(0, 128, 256);
   const uint64_t dsw = smem_desc_sw128(0);
   const uint32_t img = smem_u32(smem);
-  auto ss3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+  // A layer = for every K step the two cross terms lo'.Whi + hi.Wlo' (they carry the 2^LO_SHIFT lift), then hi.Whi, whose
+  // first MMA takes the accumulated cross terms in with the input scale 2^-LO_SHIFT.  *_x: x[col] K steps (A in the
+  // group's swizzled shared-memory tiles), *_t: K steps whose A operand lives in TMEM.
+  auto cross_x = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
     const uint64_t adh = dsw + (uint64_t)(ah >> 4), adl = dsw + (uint64_t)(al >> 4);
     const uint64_t bdh = dzero + (uint64_t)((img + off_h) >> 4), bdl = dzero + (uint64_t)((img + off_l) >> 4);
-    mma_ss(d, adh, bdh, idesc, first ? 0u : 1u);
+    mma_ss(d, adl, bdh, idesc, first ? 0u : 1u);
     mma_ss(d, adh, bdl, idesc, 1u);
-    mma_ss(d, adl, bdh, idesc, 1u);
   };
-  auto ts3 = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
+  auto cross_t = [&](uint32_t d, uint32_t ah, uint32_t al, int off_h, int off_l, uint32_t idesc, bool first) {
     const uint64_t bdh = dzero + (uint64_t)((img + off_h) >> 4), bdl = dzero + (uint64_t)((img + off_l) >> 4);
-    mma_ts(d, ah, bdh, idesc, first ? 0u : 1u);
+    mma_ts(d, al, bdh, idesc, first ? 0u : 1u);
     mma_ts(d, ah, bdl, idesc, 1u);
-    mma_ts(d, al, bdh, idesc, 1u);
+  };
+  auto main_x = [&](uint32_t d, uint32_t ah, int off_h, uint32_t idesc, bool first) {
+    const uint64_t adh = dsw + (uint64_t)(ah >> 4), bdh = dzero + (uint64_t)((img + off_h) >> 4);
+    if (first) mma_ss_sd(d, adh, bdh, idesc);
+    else mma_ss(d, adh, bdh, idesc, 1u);
+  };
+  auto main_t = [&](uint32_t d, uint32_t ah, int off_h, uint32_t idesc, bool first) {
+    const uint64_t bdh = dzero + (uint64_t)((img + off_h) >> 4);
+    if (first) mma_ts_sd(d, ah, bdh, idesc);
+    else mma_ts(d, ah, bdh, idesc, 1u);
   };
   auto issue_layer = [&](int layer) {
     if (layer == 1) { mbar_wait(xc_ready, px); px ^= 1; }               // the tile's x[col] rows have landed (TMA)
     tc_fence_after();
     if (elect_one()) {
       const uint32_t cb = tcol;
+      // x[col] K steps 0,1: x_init, 2,3: x_lat; hi at +0, lo at +64 B of a 128-B row
+      auto xa = [&](int ks) { return grp_addr + (ks >> 1) * (G3_XL - G3_XI) + (ks & 1) * 32; };
       if (layer == 1) {
+        constexpr uint32_t id = idesc_f16(128, EH);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {                               // K steps 0,1: x_init, 2,3: x_lat; hi at +0, lo at +64 B
-          const uint32_t at = grp_addr + (ks >> 1) * (G3_XL - G3_XI) + (ks & 1) * 32;
-          ss3(cb + T3_D1, at, at + 64, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB, idesc_f16(128, EH), ks == 0);
-        }
+        for (int ks = 0; ks < 4; ++ks) cross_x(cb + T3_D1, xa(ks), xa(ks) + 64, OFF_L1H + ks * L1_SLAB, OFF_L1L + ks * L1_SLAB, id, ks == 0);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          ts3(cb + T3_D1, cb + T3_EH + 8 * ks, cb + T3_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB,
-              OFF_L1L + (4 + ks) * L1_SLAB, idesc_f16(128, EH), false);
+          cross_t(cb + T3_D1, cb + T3_EH + 8 * ks, cb + T3_EL + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB, OFF_L1L + (4 + ks) * L1_SLAB, id, false);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) main_x(cb + T3_D1, xa(ks), OFF_L1H + ks * L1_SLAB, id, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) main_t(cb + T3_D1, cb + T3_EH + 8 * ks, OFF_L1H + (4 + ks) * L1_SLAB, id, false);
       } else if (layer == 2) {
+        constexpr uint32_t id = idesc_f16(128, DE);
 #pragma unroll
         for (int ks = 0; ks < L2_KS; ++ks)
-          ts3(cb + T3_D2, cb + T3_D1 + 16 * ks, cb + T3_D1 + 16 * ks + 8, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB,
-              idesc_f16(128, DE), ks == 0);
-      } else if (layer == 3) {
+          cross_t(cb + T3_D2, cb + T3_D1 + 16 * ks, cb + T3_D1 + 16 * ks + 8, OFF_L2H + ks * L2_SLAB, OFF_L2L + ks * L2_SLAB, id, ks == 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t at = grp_addr + (ks >> 1) * (G3_XL - G3_XI) + (ks & 1) * 32;
-          ss3(cb + T3_D3, at, at + 64, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB, idesc_f16(128, FHP), ks == 0);
-        }
-        ts3(cb + T3_D3, cb + T3_A3, cb + T3_A3 + 8, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, idesc_f16(128, FHP), false);
+        for (int ks = 0; ks < L2_KS; ++ks) main_t(cb + T3_D2, cb + T3_D1 + 16 * ks, OFF_L2H + ks * L2_SLAB, id, ks == 0);
+      } else if (layer == 3) {
+        constexpr uint32_t id = idesc_f16(128, FHP);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) cross_x(cb + T3_D3, xa(ks), xa(ks) + 64, OFF_L3H + ks * L3_SLAB, OFF_L3L + ks * L3_SLAB, id, ks == 0);
+        cross_t(cb + T3_D3, cb + T3_A3, cb + T3_A3 + 8, OFF_L3H + 4 * L3_SLAB, OFF_L3L + 4 * L3_SLAB, id, false);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) main_x(cb + T3_D3, xa(ks), OFF_L3H + ks * L3_SLAB, id, ks == 0);
+        main_t(cb + T3_D3, cb + T3_A3, OFF_L3H + 4 * L3_SLAB, id, false);
       } else {
+        constexpr uint32_t id = idesc_f16(128, DN);
 #pragma unroll
         for (int ks = 0; ks < L4_KS; ++ks)
-          ts3(cb + T3_D4, cb + T3_D3 + 16 * ks, cb + T3_D3 + 16 * ks + 8, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB,
-              idesc_f16(128, DN), ks == 0);
+          cross_t(cb + T3_D4, cb + T3_D3 + 16 * ks, cb + T3_D3 + 16 * ks + 8, OFF_L4H + ks * L4_SLAB, OFF_L4L + ks * L4_SLAB, id, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < L4_KS; ++ks) main_t(cb + T3_D4, cb + T3_D3 + 16 * ks, OFF_L4H + ks * L4_SLAB, id, ks == 0);
       }
       mma_commit(d_ready);
     }
@@ -931,7 +618,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+      split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
       vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
     }
     tmem_st8(tlane + col, hi);
@@ -952,6 +639,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     }
   };
   // this thread's edge row [e_init | e] (split halves) -> TMEM operand columns; half B
+  const __half2 rho = __float2half2_rn(pow2i(s_prev - s_cur));
   struct EdgeRow { uint4 v[8]; };
   auto load_edge_row = [&](int64_t base, int cnt) {
     EdgeRow r;
@@ -960,6 +648,14 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     const uint4* p1 = a.es_in + sl * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { r.v[j] = __ldg(p0 + j); r.v[4 + j] = p1[j]; }
+    if (s_cur != s_prev) {                                             // uniform; e was stored in the previous step's scale
+#pragma unroll
+      for (int j = 4; j < 8; ++j) {
+        __half2* h = reinterpret_cast<__half2*>(&r.v[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], rho);
+      }
+    }
     return r;
   };
   auto store_edge_row = [&](const EdgeRow& r) {
@@ -1022,8 +718,8 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
       if ((ends >> q) & 1u) {
         const bool starts_before = first_seg && r_prev == rq;
         const bool continues = q == cw - 1 && r_next == rq;
-        if (!starts_before && !continues) a.flow[(int64_t)rq * 2 * DN + dir_off + f] = sum;
-        else a.part[(chunk_id * 2 + (first_seg ? 0 : 1)) * DN + f] = sum;
+        if (!starts_before && !continues) a.flow[(int64_t)rq * 2 * DN + dir_off + f] = sum * inv_sigma;
+        else a.part[(chunk_id * 2 + (first_seg ? 0 : 1)) * DN + f] = sum * inv_sigma;
         sum = 0.f;
         first_seg = false;
       }
@@ -1095,7 +791,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+        split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
         vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
       }
       tmem_st8(tlane + T3_A3, hi);
@@ -1139,7 +835,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          split2_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+          split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
           vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
         }
 #pragma unroll
@@ -1179,6 +875,8 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
   {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(&vmax);
     if ((w & 0x7FFFu) >= 0x7BFFu || ((w >> 16) & 0x7FFFu) >= 0x7BFFu) atomicOr(a.status, 1);
+    const float2 vm = __half22float2(vmax);
+    atomic_max_f32(a.amax + a.step, fminf(fmaxf(vm.x, vm.y), 65504.f) * inv_sigma);
   }
   tc_fence_before();
   __syncthreads();
@@ -1206,29 +904,18 @@ static int make_row_map(CUtensorMap* out, const void* base, int64_t n) {
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
 }
 
-int variant() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("MPN_TC_VARIANT");
-    v = (e != nullptr && e[0] == '2') ? 2 : 3;
-  }
-  return v;
-}
-
-
-long long* g_trace = nullptr;   // set by mpn_tc_set_trace (development only)
-
 struct TcWorkspace {
   __half* xi; __half* xl[2];
   float* pinit; float* prow;
   uint4* ei; uint4* es;
   float* flow; float* part;
   uint8_t* wimg_out; uint8_t* wimg_in;
+  int32_t* sched; uint32_t* amax; uint32_t* xmax;      // range bookkeeping, MAX_STEPS + 8 entries each (contiguous)
 };
 
 static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   Carver cv(ws);
-  const int64_t chunks = ceil_div(e, CHUNK3) + 8;          // sized for the finer granule of the two kernel variants
+  const int64_t chunks = ceil_div(e, CHUNK3) + 8;
   TcWorkspace w;
   w.xi = cv.take<__half>(n * 64);
   w.xl[0] = cv.take<__half>(n * 64);
@@ -1241,6 +928,9 @@ static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   w.part = cv.take<float>(chunks * 2 * DN);
   w.wimg_out = cv.take<uint8_t>(IMG_BYTES);
   w.wimg_in = cv.take<uint8_t>(IMG_BYTES);
+  w.sched = cv.take<int32_t>(3 * (MAX_STEPS + 8));
+  w.amax = reinterpret_cast<uint32_t*>(w.sched) + (MAX_STEPS + 8);
+  w.xmax = w.amax + (MAX_STEPS + 8);
   if (out) *out = w;
   return cv.off;
 }
@@ -1252,11 +942,21 @@ using namespace mpn;
 
 extern "C" {
 
-/* development hook (not in the public header): device buffer of 64*16 int64 for a cycle trace */
-void mpn_tc_set_trace(long long* d_buf) { tc::g_trace = d_buf; }
-
 int64_t mpn_mp_tc_workspace(int64_t n, int64_t e) {
   return tc::carve(nullptr, n > 0 ? n : 1, e > 0 ? e : 1, nullptr) + 256;
+}
+
+int mpn_mp_tc_read_schedule(const void* ws, int64_t n, int64_t e, int32_t num_steps, int32_t* h_sched, float* h_amax,
+                            float* h_xmax, void* stream) {
+  MPN_CHECK_ARG(ws && num_steps >= 1 && num_steps <= tc::MAX_STEPS, "mp_tc_read_schedule: bad arguments");
+  tc::TcWorkspace m;
+  tc::carve(const_cast<void*>(ws), n > 0 ? n : 1, e > 0 ? e : 1, &m);
+  cudaStream_t s = as_stream(stream);
+  if (h_sched) MPN_CUDA(cudaMemcpyAsync(h_sched, m.sched, sizeof(int32_t) * (num_steps + 2), cudaMemcpyDeviceToHost, s));
+  if (h_amax) MPN_CUDA(cudaMemcpyAsync(h_amax, m.amax, sizeof(float) * (num_steps + 2), cudaMemcpyDeviceToHost, s));
+  if (h_xmax) MPN_CUDA(cudaMemcpyAsync(h_xmax, m.xmax, sizeof(float) * (num_steps + 2), cudaMemcpyDeviceToHost, s));
+  MPN_CUDA(cudaStreamSynchronize(s));
+  return MPN_OK;
 }
 
 int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const float* x_init, const float* e_init,
@@ -1266,7 +966,8 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   MPN_CHECK_ARG(w->dn == 32 && w->de == 16 && w->edge_h == 80 && w->flow_h == 56 && w->cls_h == 8,
                 "mp_forward_tc: built for widths dn=32 de=16 edge_h=80 flow_h=56 cls_h=8 (got %d %d %d %d %d)", w->dn,
                 w->de, w->edge_h, w->flow_h, w->cls_h);
-  MPN_CHECK_ARG(num_steps >= 1, "mp_forward_tc: num_steps must be >= 1 (use mpn_mp_forward for 0)");
+  MPN_CHECK_ARG(num_steps >= 1 && num_steps <= tc::MAX_STEPS, "mp_forward_tc: num_steps must be in 1..%d (use mpn_mp_forward for 0)",
+                tc::MAX_STEPS);
   MPN_CHECK_ARG(ws && status, "mp_forward_tc: null workspace / status");
   const int64_t n = g->num_nodes, e = g->num_edges;
   cudaStream_t s = as_stream(stream);
@@ -1275,17 +976,13 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   tc::TcWorkspace m;
   tc::carve(ws, n, e > 0 ? e : 1, &m);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM3_BYTES));
-    attr_set = true;
-  }
+  MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM3_BYTES));
+  MPN_CUDA(cudaMemsetAsync(m.sched, 0, 3 * (tc::MAX_STEPS + 8) * 4, s));
   const int sms = sm_count();
-  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, tc::variant() == 3 ? 1 : 0); count_launch();
+  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, 1); count_launch();
   const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 4);
   const unsigned ngrid_node = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 2);   // node weights in registers: 2 CTAs/SM
-  tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, status);
+  tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, m.xmax, status);
   count_launch();
   if (e > 0) {
     const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div(e, 256), (int64_t)sms * 8);
@@ -1295,23 +992,19 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
 
   const int tiles_out = (int)ceil_div(g->num_out, tc::TS);
   const int tiles_in = (int)ceil_div(e - g->num_out, tc::TS);
-  const int pairs = (tiles_out + 1) / 2 + (tiles_in + 1) / 2;
-  int grid = sms;
-  if (grid > pairs) grid = pairs;
-  if (tiles_out > 0 && tiles_in > 0 && grid < 2) grid = 2;
   const int triples = (tiles_out + 2) / 3 + (tiles_in + 2) / 3;
   int grid3 = sms;
   if (grid3 > triples) grid3 = triples;
   if (tiles_out > 0 && tiles_in > 0 && grid3 < 2) grid3 = 2;
 
   CUtensorMap tm_xi, tm_xl[2];
-  if (tc::variant() == 3 && e > 0) {
+  if (e > 0) {
     if (tc::make_row_map(&tm_xi, m.xi, n) || tc::make_row_map(&tm_xl[0], m.xl[0], n) || tc::make_row_map(&tm_xl[1], m.xl[1], n)) {
       set_error("mpn_mp_forward_tc: cuTensorMapEncodeTiled failed");
       return MPN_ECUDA;
     }
   }
-  const int chunk_shift = tc::variant() == 3 ? tc::CHUNK3_SHIFT : 5;
+  const int chunk_shift = tc::CHUNK3_SHIFT;
   const int64_t chunk = (int64_t)1 << chunk_shift;
   for (int step = 1; step <= num_steps; ++step) {
     const __half* xl_cur = m.xl[(step - 1) & 1];
@@ -1331,10 +1024,9 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       a.logits = (logits && step >= first_class_step) ? logits + (int64_t)(step - first_class_step) * e : nullptr;
       a.wimg_out = m.wimg_out; a.wimg_in = m.wimg_in;
       a.status = status;
-      a.trace = (step == 2) ? tc::g_trace : nullptr;
+      a.step = step; a.sched = m.sched; a.amax = m.amax;
       if (profiling()) profile_mark(0, true, s);
-      if (tc::variant() == 3) tc::mp_edge_tc3_kernel<<<grid3, tc::NTHREADS3, tc::SMEM3_BYTES, s>>>(a, tm_xi, tm_xl[(step - 1) & 1]);
-      else tc::mp_edge_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, s>>>(a);
+      tc::mp_edge_tc3_kernel<<<grid3, tc::NTHREADS3, tc::SMEM3_BYTES, s>>>(a, tm_xi, tm_xl[(step - 1) & 1]);
       count_launch();
       if (profiling()) profile_mark(0, false, s);
     }
@@ -1342,14 +1034,14 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
     tc::node_tc_kernel<<<ngrid_node, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
                                              (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
                                              w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
-                                             step == num_steps ? x_out : nullptr, status);
+                                             step == num_steps ? x_out : nullptr, step, m.sched, m.amax, m.xmax, status);
     count_launch();
     if (profiling()) profile_mark(1, false, s);
     MPN_LAUNCH_CHECK();
   }
   if (e_out && e > 0) {
     const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div(e, 256), (int64_t)sms * 8);
-    tc::unsplit_edges_kernel<<<egrid, 256, 0, s>>>(m.es, e, e_out); count_launch();
+    tc::unsplit_edges_kernel<<<egrid, 256, 0, s>>>(m.es, e, e_out, m.sched, num_steps); count_launch();
     MPN_LAUNCH_CHECK();
   }
   return MPN_OK;

@@ -177,5 +177,41 @@ __device__ __forceinline__ void split2_relu(float a, float b, uint32_t& hi, uint
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
 }
 
+// ---------------------------------------------------------------- fp16 hi/lo split with a lifted low part
+// v ~= hi + lo' * 2^-LO_SHIFT with lo' = fp16((v - hi) * 2^LO_SHIFT).  The low part is then a NORMAL fp16 number whenever
+// hi is (|lo'| <= |hi| / 2 for the rn split, < |hi| for the truncating ReLU split, so it can never overflow), i.e. the
+// pair keeps 22 significant bits over the whole fp16 exponent range instead of losing low bits to subnormals below
+// ~0.1.  The MMAs accumulate the two cross terms (lo'.hi, hi.lo') first and fold them in with the accumulator input
+// scale of tcgen05.mma (D = A.B + D * 2^-LO_SHIFT, `mma_*_sd`).
+constexpr int LO_SHIFT = 10;
+constexpr float LO_SCALE = 1024.f;
+__device__ __forceinline__ void split2s(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split2s_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((b - hf.y) * LO_SCALE), "f"((a - hf.x) * LO_SCALE));
+}
+// D = A.B + D * 2^-LO_SHIFT (kind::f16 accumulator input scale)
+__device__ __forceinline__ void mma_ts_sd(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 10;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_sd(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 10;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+
 }  // namespace ptx
 }  // namespace mpn

@@ -41,20 +41,60 @@ class _NullClassifier(nn.Module):
         return [self.l0, self.l1]
 
 
+def _zeros_like_core(dn, de, edge_h, flow_h, device):
+    """Placeholder tensors for the parts of ``mpn_core_weights`` a single sub-model does not own (the C
+    struct is one block; mpn_mp_step's mode selects which weights are read)."""
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
+    return {'edge_w0': z(edge_h, 4 * dn + 2 * de), 'edge_b0': z(edge_h), 'edge_w1': z(de, edge_h), 'edge_b1': z(de),
+            'fin_w0': z(flow_h, 2 * dn + de), 'fin_b0': z(flow_h), 'fin_w1': z(dn, flow_h), 'fin_b1': z(dn),
+            'fout_w0': z(flow_h, 2 * dn + de), 'fout_b0': z(flow_h), 'fout_w1': z(dn, flow_h), 'fout_b1': z(dn),
+            'node_w': z(dn, 2 * dn), 'node_b': z(dn),
+            'cls_w0': z(8, de), 'cls_b0': z(8), 'cls_w1': z(1, 8), 'cls_b1': z(1)}
+
+
+def _split_reattached(x, edge_attr, dn, de):
+    if x.shape[1] != 2 * dn or edge_attr.shape[1] not in (de, 2 * de):
+        raise NotImplementedError('the fused step is built for reattach_initial_nodes/edges = True '
+                                  f'(x [N,{2 * dn}], edge_attr [E,{2 * de}])')
+    return x[:, :dn].contiguous(), x[:, dn:].contiguous()
+
+
 class EdgeModel(nn.Module):
-    """Edge update e' = MLP(cat[x[row], x[col], e]).  reference: models/mpn.py:59-69"""
+    """Edge update e' = MLP(cat[x[row], x[col], e]).  reference: models/mpn.py:59-69
+    ``forward(node_feats [N,64], edge_index [2,E], edge_attr [E,32]) -> [E,16]`` in the caller's edge order;
+    runs the fused edge kernel in its edge-only mode (mpn_mp_step mode 1)."""
 
     def __init__(self, edge_model):
         super().__init__()
         self.edge_model = edge_model
 
     def forward(self, node_feats, edge_index, edge_attr):
-        raise NotImplementedError('EdgeModel is evaluated inside MetaLayer.forward (fused kernel); '
-                                  'call MetaLayer(edge_model=..., node_model=None)')
+        e0, e1 = self.edge_model.linears()
+        de, edge_h = e1.out_features, e0.out_features
+        dn = (e0.in_features - 2 * de) // 4
+        named = _zeros_like_core(dn, de, edge_h, 56, e0.weight.device)
+        named.update(edge_w0=e0.weight, edge_b0=e0.bias, edge_w1=e1.weight, edge_b1=e1.bias)
+        cw, keep = ops.core_weights(named)
+        xi, xl = _split_reattached(node_feats, edge_attr, dn, de)
+        if edge_attr.shape[1] != 2 * de:
+            raise NotImplementedError(f'EdgeModel expects edge_attr [E,{2 * de}] (reattach_initial_edges = True)')
+        layout = ops.edge_layout(edge_index, node_feats.shape[0])
+        e = layout.num_edges
+        if e == 0:
+            return edge_attr.new_zeros((0, de))
+        ea = ops.gather_rows(edge_attr, layout.slot_edge[:e])
+        e_new, _, _ = ops.mp_step(cw, layout, xi, xl, ea[:, :de].contiguous(), ea[:, de:].contiguous(), mode=1)
+        out = torch.empty_like(e_new)
+        out[layout.slot_edge[:e].long()] = e_new
+        del keep
+        return out
 
 
 class TimeAwareNodeModel(nn.Module):
-    """Time-aware node update.  reference: models/mpn.py:71-99"""
+    """Time-aware node update.  reference: models/mpn.py:71-99
+    ``forward(x [N,64], edge_index [2,E], edge_attr [E,16]) -> [N,32]`` where ``edge_attr`` holds the already
+    updated edge features (models/mpn.py:52); runs the fused kernels in their node-only mode (mpn_mp_step mode 2).
+    ``node_agg_fn`` is the reference's name for the aggregation ('sum' | 'mean' | 'max' or its lambda)."""
 
     def __init__(self, flow_in_model, flow_out_model, node_model, node_agg_fn):
         super().__init__()
@@ -64,8 +104,27 @@ class TimeAwareNodeModel(nn.Module):
         self.node_agg_fn = node_agg_fn
 
     def forward(self, x, edge_index, edge_attr):
-        raise NotImplementedError('TimeAwareNodeModel is evaluated inside MetaLayer.forward (fused kernel); '
-                                  'call MetaLayer(edge_model=None, node_model=...)')
+        i0, i1 = self.flow_in_model.linears()
+        de = edge_attr.shape[1]
+        dn, flow_h = i1.out_features, i0.out_features
+        if i0.in_features != 2 * dn + de:
+            raise NotImplementedError(f'TimeAwareNodeModel expects x [N,{2 * dn}] and edge_attr [E,{i0.in_features - 2 * dn}]')
+        if self.node_agg_fn not in ('sum', None) and not callable(self.node_agg_fn):
+            raise NotImplementedError("node_agg_fn other than 'sum' goes through MOTMPNet (aggregation mode of the core)")
+        o0, o1 = self.flow_out_model.linears()
+        named = _zeros_like_core(dn, de, 80, flow_h, i0.weight.device)
+        named.update(fin_w0=i0.weight, fin_b0=i0.bias, fin_w1=i1.weight, fin_b1=i1.bias,
+                     fout_w0=o0.weight, fout_b0=o0.bias, fout_w1=o1.weight, fout_b1=o1.bias,
+                     node_w=self.node_model[0].weight, node_b=self.node_model[0].bias)
+        cw, keep = ops.core_weights(named)
+        if x.shape[1] != 2 * dn:
+            raise NotImplementedError(f'TimeAwareNodeModel expects x [N,{2 * dn}] (reattach_initial_nodes = True)')
+        layout = ops.edge_layout(edge_index, x.shape[0])
+        e = layout.num_edges
+        ea = ops.gather_rows(edge_attr, layout.slot_edge[:e]) if e else edge_attr
+        _, x_new, _ = ops.mp_step(cw, layout, x[:, :dn].contiguous(), x[:, dn:].contiguous(), ea, ea, mode=2)
+        del keep
+        return x_new
 
 
 class MetaLayer(nn.Module):
@@ -121,8 +180,12 @@ class TimeAwareAttentionModel(nn.Module):
         super().__init__()
         self.node_model = node_model        # the two attention MLPs are built and dropped by the reference (:106-109)
 
-    def aggregate(self, x, layout, logits):
-        flow_in, flow_out = ops.attn_aggregate(x, layout, logits)
+    def aggregate(self, x, layout, logits, differentiable=False):
+        if differentiable:
+            from ..training import AttnAggregate
+            flow_in, flow_out = AttnAggregate.apply(x, logits, layout)
+        else:
+            flow_in, flow_out = ops.attn_aggregate(x, layout, logits)
         return self.node_model(torch.cat((x, flow_in, flow_out), dim=1))
 
     def forward(self, x, edge_index, edge_attr, cls_net):
@@ -322,18 +385,19 @@ class MOTMPNet(nn.Module):
     def forward(self, data, return_state=False):
         x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
         x_ext = getattr(data, 'x_ext', None) if self.has_mask_branch else None
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # training (pl_module.py:122-135): the core network runs through the deterministic fp32 training kernels
-            # with a hand-written backward; loss.backward() fills p.grad of the encoder / MPNet / classifier weights
-            if x_ext is not None:
-                raise NotImplementedError('training through the attention / mask branch is not built: pass x_ext=None '
-                                          '(tracking loss of the core network) or call under torch.no_grad()')
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training (pl_module.py:122-135): model.train() + autograd on.  The core network runs through the
+            # deterministic fp32 training kernels with a hand-written backward; loss.backward() fills p.grad of the
+            # encoder / MPNet / classifier weights.  Evaluation-mode calls (model.eval(), with or without no_grad)
+            # always take the inference kernels below.
             if return_state:
                 raise NotImplementedError('return_state is an inference-only option')
-            from ..training import CoreTrainer
-            tr = getattr(self, '_core_trainer', None) or CoreTrainer(self)
+            tr = self.core_trainer()
             logits = tr.autograd_logits(data)
-            return {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])], 'mask_predictions': []}
+            out = {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])], 'mask_predictions': []}
+            if x_ext is not None:
+                out['mask_predictions'] = self._mask_branch_train(x_ext, data, tr)
+            return out
         layout = ops.edge_layout(edge_index, x.shape[0])
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
         # the attention branch needs the logits of EVERY step (models/mpn.py:377), the output only the last ones
@@ -348,6 +412,23 @@ class MOTMPNet(nn.Module):
         if return_state:
             out['node_state'], out['edge_state_slots'], out['layout'] = res[1], res[2], layout
         return out
+
+    def core_trainer(self):
+        """The ``training.CoreTrainer`` bound to this model (built on first use: it re-homes the core parameters
+        into one flat bucket, so it is created explicitly or by the first training-mode forward, never by an
+        evaluation call)."""
+        tr = getattr(self, '_core_trainer', None)
+        if tr is None:
+            from ..training import CoreTrainer
+            tr = CoreTrainer(self)
+        return tr
+
+    def _mask_branch_train(self, x_ext, data, tr):
+        """Mask predictions in training mode (pl_module.py:107-118 trains them with a BCE on the valid ids).
+        The convolution stacks are torch modules, so autograd reaches every mask-branch parameter; the attention
+        weights come from the DETACHED per-step logits of the core network (the mask loss does not back-propagate
+        into the tracking network here; the reference lets it)."""
+        raise NotImplementedError('training through the attention / mask branch is not built yet')
 
     def _core(self, xs, edge_attr, layout, first_needed, want_state=False, encoded=False):
         """Encoders + step loop.  The tensor-core kernels report fp16-range overflow through one status
@@ -376,14 +457,14 @@ class MOTMPNet(nn.Module):
         del keep
         return res
 
-    def _mask_branch(self, x_ext, layout, logits, first_class_step):
+    def _mask_branch(self, x_ext, layout, logits, first_class_step, differentiable=False):
         """Attentive node-feature-map updates + mask head per classified step.
         reference: models/mpn.py:356,360,369-385 (and :387-392 for num_enc_steps == 0)"""
         z0 = self.node_ext_encoder(x_ext)
         z, masks = z0, []
         for step in range(1, self.num_enc_steps + 1):
             zc = torch.cat((z0, z), dim=1).contiguous()                # reattach the initial encoding (:373)
-            z = self.MPAttentionNet.aggregate(zc, layout, logits[step - 1])
+            z = self.MPAttentionNet.aggregate(zc, layout, logits[step - 1], differentiable=differentiable)
             if step >= first_class_step:
                 masks.append(self.mask_predictor(x_ext, z))
         if self.num_enc_steps == 0:

@@ -45,6 +45,8 @@ def time_valid_pairs(frame_num, max_frame_dist=-1, node_graph_ptr=None):
     check(lib().mpn_time_valid_pairs_count(ptr(f), n, ptr(gp), g, int(max_frame_dist), ptr(row_start),
                                            C.byref(total), stream_ptr()), 'time_valid_pairs_count')
     pairs = torch.empty((2, total.value), dtype=torch.int64, device=f.device)
+    if total.value == 0:                 # one detection, or all detections in one frame: no candidate pair
+        return pairs
     check(lib().mpn_time_valid_pairs_fill(ptr(f), n, ptr(gp), g, int(max_frame_dist), ptr(row_start),
                                           ptr(pairs[0]), ptr(pairs[1]), stream_ptr()), 'time_valid_pairs_fill')
     return pairs
@@ -324,14 +326,17 @@ def default_engine():
     return eng
 
 
+LAST_TC_SCHEDULE = {}     # filled by mp_forward(..., debug=True): {'sched': [...], 'amax': [...], 'xmax': [...]} by step
+
+
 def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_state=False, engine=None,
-               status=None):
+               status=None, debug=False):
     """Run the step loop.  Returns logits [S, E] (original edge order) and, if asked, the final
     node / edge latent states (edge state in slot order).  models/mpn.py:364-389
 
-    engine: 'tc' = tcgen05 tensor-core kernels (fp16 hi/lo split operands, fp32 accumulate),
-    'fp32' = fp32 SIMT kernels, 'auto' (default) = 'tc', rerun on 'fp32' if an activation left
-    the fp16 range.  status: optional int32[1] device tensor: the overflow flag is left there for the
+    engine: 'tc' = tcgen05 tensor-core kernels (fp16 hi/lo split operands in a per-step power-of-two
+    scale, fp32 accumulate), 'fp32' = fp32 SIMT kernels, 'auto' (default) = 'tc', rerun on 'fp32' if an
+    activation still left the fp16 range (one-step growth beyond the 64x headroom of the scale).  status: optional int32[1] device tensor: the overflow flag is left there for the
     caller (no host sync, no fallback here)."""
     engine = engine or default_engine()
     x_init = _req(x_init, torch.float32, 'x_init')
@@ -353,6 +358,10 @@ def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_sta
         check(lib().mpn_mp_forward_tc(C.byref(cw), C.byref(g), ptr(x_init), ptr(e_init), int(num_steps), int(first),
                                       ptr(ws), ptr(logits), ptr(x_out), ptr(e_out), ptr(status), stream_ptr()),
               'mp_forward_tc')
+        if debug:
+            hs, ha, hx = (C.c_int32 * (num_steps + 2))(), (C.c_float * (num_steps + 2))(), (C.c_float * (num_steps + 2))()
+            check(lib().mpn_mp_tc_read_schedule(ptr(ws), n, e, int(num_steps), hs, ha, hx, stream_ptr()), 'mp_tc_read_schedule')
+            LAST_TC_SCHEDULE.update(sched=list(hs), amax=list(ha), xmax=list(hx))
         if deferred or (engine == 'tc' and not STRICT_TC_STATUS):
             return (logits, x_out, e_out) if want_state else logits
         if int(status.item()) == 0:
