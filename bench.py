@@ -21,6 +21,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from mpntrackseg_b200 import synth  # noqa: E402
@@ -54,6 +55,32 @@ def workload_name(a):
     feats = 'x[N,2048]' if a.pooled else 'x[N,2048,8,4]'
     return (f'configs[1]: MOTS20-scale windows T={a.frames} D={a.dets} k={a.k}, {NUM_STEPS_MP} MP steps, '
             f'{feats}, full forward incl. ReID-distance KNN build; {a.graphs} windows per GPU per step')
+
+
+def config_dict(a, world):
+    """The `config` object of the JSON line; identical in both arms (--impl b200 / reference)."""
+    return {'workload': workload_name(a),
+            'parallelism': f'independent windows sharded over {world} GPU(s), no collective',
+            'l2_policy': 'inputs larger than L2 (node features 590 MB per window)' if not a.pooled
+            else 'pooled inputs (18 MB per window); MP state is L2-resident by nature'}
+
+
+def pin_to_gpu_numa(gpu_index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU BEFORE any page-locked buffer is allocated,
+    so that the host side of every H2D copy reads node-local memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu}
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def make_windows(a, rank, world):
@@ -114,7 +141,7 @@ def run_reference(a):
     base, ms = cpu_sample(a, a.steps, a.warmup)
     line = dict(impl='reference', metric=METRIC, value=base['value'], unit=UNIT, n_gpus=a.gpus, steps=a.steps,
                 warmup=a.warmup, ms_per_step=ms * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32', data='synthetic', config={'workload': workload_name(a), 'sample': base['sample']},
+                dtype='f32', data='synthetic', config=config_dict(a, a.gpus),
                 cpu_baseline=base,
                 e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 graphs_per_s=1.0 / ms)
@@ -183,6 +210,7 @@ def run_b200(a):
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _cabi.lib()
@@ -227,10 +255,9 @@ def run_b200(a):
 
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def step_e2e():
-        """Same through the public API from pinned host buffers: the small per-detection tables are
-        copied first, the big node-feature tensors follow on a copy stream and each window's encoder
-        waits only for its own x (H2D overlaps the graph build); logits are read back."""
+    def step_e2e_raw():
+        """Raw-map arm (second number): the reference's stored [N,2048,8,4] node-core maps go host -> device every
+        step (9.5 GB per 16 windows) and are pooled on the GPU; PCIe-bound by construction."""
         main = torch.cuda.current_stream()
         events = []
         with torch.cuda.stream(copy_stream):
@@ -260,6 +287,74 @@ def run_b200(a):
         res = out.logits[-1].cpu()                                    # D2H of the result (last step's logits)
         assert not flags.any().item(), 'fp16 overflow in the encoder (would need the fp32 rerun)'
         return batch, res
+
+    # ---- end-to-end arm through the embedding store: the job's windows are written once to a
+    #      per-frame store (ReID [n,1+256] and the pooled node-core variant [n,1+2048] of EmbeddingStore.pool) and
+    #      packed into page-locked memory (SequenceEmbeddings).  Every timed step copies the detection table, the
+    #      ReID vectors and the pooled node-core vectors host -> device, builds the graphs, runs the forward and reads
+    #      the last step's logits back; the copy of step i+1 overlaps the compute of step i (two device buffer sets).
+    import shutil
+    import tempfile
+    import pandas as pd
+    from mpntrackseg_b200.data.embedding_store import EmbeddingStore, SequenceEmbeddings
+    tmp = tempfile.mkdtemp(prefix=f'mpn_store_r{rank}_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    seq_info = {'seq_path': tmp, 'det_file_name': 'synthetic_det', 'fps': fps}
+    dsx = dict(ds, reid_embeddings_dir='reid', node_core_embeddings_dir='node_core', node_ext_embeddings_dir=None)
+    store = EmbeddingStore(seq_info)
+    n_tot = node_ptr[-1]
+    table = {k: cols[k].numpy().copy() for k in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+    for g in range(len(wins)):                                        # one table for the job: window g owns its own frames
+        table['frame'][node_ptr[g]:node_ptr[g + 1]] += g * (a.frames + 1)
+    table['detection_id'] = np.arange(n_tot, dtype=np.int64)
+    det_df = pd.DataFrame(table)
+    store.write('reid', table['frame'], table['detection_id'], cols['reid'])
+    # the pooled store (what EmbeddingStore.pool writes from the reference's [n,1+2048,8,4] files; here the maps are
+    # already on the device, so they are pooled there by the same kernel and only the pooled frames are written)
+    pooled_rows = torch.cat([x if x.dim() == 2 else ops.avgpool(x) for x in devin['x']]).cpu()
+    store.write('node_core_pooled', table['frame'], table['detection_id'], pooled_rows)
+    del pooled_rows
+    seq = SequenceEmbeddings(det_df, seq_info, dsx, pooled=True, pin_memory=True)
+    shutil.rmtree(tmp, ignore_errors=True)
+    host_tab = {k: torch.from_numpy(table[k]).pin_memory() for k in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+    e2e_host = dict(host_tab, reid=seq.reid, x=seq.node_core)
+    e2e_h2d = sum(t.numel() * t.element_size() for t in e2e_host.values())
+    bufsets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in e2e_host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    out_host = [None, None]
+
+    def e2e_upload(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[b])                           # the compute that last read this buffer set is done
+            for k, v in e2e_host.items():
+                bufsets[b][k].copy_(v, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_pipeline(steps):
+        main = torch.cuda.current_stream()
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        for b in range(2):
+            free[b].record(main)
+        e2e_upload(0)
+        for i in range(steps):
+            b = i & 1
+            if i + 1 < steps:
+                e2e_upload(i + 1)
+            main.wait_event(ready[b])
+            inputs = bufsets[b]
+            batch = build_graph_batch(inputs, node_ptr, ds, fps, device=dev)
+            with torch.no_grad():
+                batch.xs = model.encode_pooled(inputs['x'], status=flags)
+                out = model.forward_batch(batch, encoded=True)
+            free[b].record(main)
+            last = out.logits[-1]
+            if out_host[b] is None or out_host[b].shape != last.shape:
+                out_host[b] = torch.empty(last.shape, dtype=last.dtype).pin_memory()
+            out_host[b].copy_(last, non_blocking=True)                 # D2H of the step's result
+        torch.cuda.synchronize()
+        assert not flags.any().item(), 'fp16 overflow in the encoder (would need the fp32 rerun)'
+        return out_host[(steps - 1) & 1]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -297,24 +392,42 @@ def run_b200(a):
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host buffers in, logits out, copies inside the timed region
-    for _ in range(max(2, a.warmup)):
-        step_e2e()
+    e2e_pipeline(max(2, a.warmup))
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    d2h = 0
-    for _ in range(a.steps):
-        _, res = step_e2e()
-        d2h = res.numel() * res.element_size()
+    res = e2e_pipeline(a.steps)
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1)
+    d2h = res.numel() * res.element_size()
+    # parity of the store arm with the device-resident arm on the same windows (same kernels, same inputs)
+    with torch.no_grad():
+        ref_last = step(devin)[1].logits[-1].cpu()
+    e2e_max_diff = float((res - ref_last).abs().max())
+
+    # ---- second number: raw [N,2048,8,4] maps from pinned memory every step (the round-1 e2e definition)
+    raw_steps = min(a.steps, 5)
+    ms_raw = None
+    if not a.pooled:
+        for _ in range(2):
+            step_e2e_raw()
+        sync_all()
+        t0.record()
+        for _ in range(raw_steps):
+            step_e2e_raw()
+        t1.record()
+        sync_all()
+        ms_raw = t0.elapsed_time(t1)
     gc.enable()
 
     from mpntrackseg_b200.sharding import reduce_step_stats
-    ms, (all_edges, all_nodes, h2d_total, d2h_total) = reduce_step_stats(ms, [edges, nodes, h2d_bytes, d2h], device=dev)
+    ms, (all_edges, all_nodes, h2d_total, d2h_total, h2d_raw_total) = reduce_step_stats(
+        ms, [edges, nodes, e2e_h2d, d2h, h2d_bytes], device=dev)
     ms_e2e, _ = reduce_step_stats(ms_e2e, [0], device=dev)
+    if ms_raw is not None:
+        ms_raw, _ = reduce_step_stats(ms_raw, [0], device=dev)
 
     if rank == 0:
         peaks = {}
@@ -331,35 +444,43 @@ def run_b200(a):
         bytes_per_launch = edges * (200 + 4 * cls_frac) + nodes * 256
         avg_ms = float(prof_ms[0]) / edge_launches
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel: only a capture of THIS workload size counts (ncu --set full of the same
+        # command, summarised in profiles/); otherwise null
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_mp_edge_tc_traffic.json')))
-            if os.environ.get('MPN_ENGINE', 'auto') != 'fp32':
-                per_edge = tr['dram_bytes_per_edge_update'] if os.environ.get('MPN_TC_VARIANT', '3') != '2' \
-                    else tr['previous_kernel']['dram_bytes_per_edge_update']
-                traffic = per_edge * edges      # ncu dram read+write per edge-update x this launch's edges
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_mp_edge_traffic.json')))
+            if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' and int(tr['edges']) == int(edges):
+                traffic = float(tr['dram_bytes_per_launch'])
         except (OSError, KeyError, ValueError):
             pass
+        kernel = 'mp_edge_tc3_kernel' if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel'
+        per_s = lambda t_ms, n_steps: NUM_STEPS_MP * all_edges * n_steps / (t_ms * 1e-3)
         line = dict(
-            metric=METRIC, value=NUM_STEPS_MP * all_edges * a.steps / (ms * 1e-3), unit=UNIT, n_gpus=world,
+            metric=METRIC, value=per_s(ms, a.steps), unit=UNIT, n_gpus=world,
             steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak',
-            vs_baseline=None, dtype='f32', data='synthetic',
-            config={'workload': workload_name(a), 'parallelism': f'windows sharded over {world} GPU(s), no collective',
-                    'l2_policy': 'inputs larger than L2 (node features 590 MB per window)' if not a.pooled
-                    else 'pooled inputs (18 MB per window); MP state is L2-resident by nature',
-                    'edges_per_gpu': edges, 'nodes_per_gpu': nodes},
+            vs_baseline=None, dtype='f32', data='synthetic', config=config_dict(a, world),
+            edges_per_gpu=edges, nodes_per_gpu=nodes,
             graphs_per_s=a.graphs * world * a.steps / (ms * 1e-3),
-            e2e=dict(value=NUM_STEPS_MP * all_edges * a.steps / (ms_e2e * 1e-3), unit=UNIT,
+            e2e=dict(value=per_s(ms_e2e, a.steps), unit=UNIT,
                      h2d_bytes_per_step=int(h2d_total), d2h_bytes_per_step=int(d2h_total),
-                     graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3)),
+                     graphs_per_s=a.graphs * world * a.steps / (ms_e2e * 1e-3), ms_per_step=ms_e2e / a.steps,
+                     source='pooled embedding store (EmbeddingStore.pool -> SequenceEmbeddings, page-locked): detection '
+                            'table + ReID [N,256] + node-core [N,2048] host->device every step, last-step logits read '
+                            'back; step i+1 uploads while step i computes',
+                     max_abs_diff_vs_device_arm=e2e_max_diff),
             gpu_launches=int(launches),
-            roofline=dict(bound='hbm', kernel=('mp_edge_tc3_kernel' if os.environ.get('MPN_TC_VARIANT', '3') != '2' else 'mp_edge_tc_kernel') if os.environ.get('MPN_ENGINE', 'auto') != 'fp32' else 'mp_edge_kernel', achieved=achieved, peak=peak, unit='GB/s',
+            roofline=dict(bound='hbm', kernel=kernel, achieved=achieved, peak=peak, unit='GB/s',
                           frac=achieved / peak if peak else None, traffic=traffic, algorithmic_bytes=bytes_per_launch,
                           peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                           avg_launch_ms=avg_ms, launches=edge_launches,
+                          node_kernel_avg_launch_ms=float(prof_ms[1]) / max(int(prof_n[1]), 1),
                           mp_phase_edge_updates_per_s=edges * edge_launches / (float(prof_ms[0] + prof_ms[1]) * 1e-3)
                           if prof_ms[0] > 0 else None),
             clocks=clocks)
+        if ms_raw is not None:
+            line['e2e_raw_maps'] = dict(value=per_s(ms_raw, raw_steps), unit=UNIT, h2d_bytes_per_step=int(h2d_raw_total),
+                                        steps=raw_steps, ms_per_step=ms_raw / raw_steps,
+                                        source='reference layout [N,2048,8,4] maps host->device every step, pooled on the GPU')
         if not a.no_cpu_baseline and world == 1:
             base, _ = cpu_sample(a, steps=3, warmup=1)
             line['cpu_baseline'] = base
@@ -388,7 +509,7 @@ def run_train(a):
     model.load_state_dict(P, strict=False)
     tr = CoreTrainer(model)
     w = synth.make_window(T=20, D=8, k=100, seed=100 + rank)
-    g = MOTGraph(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': w.fps}, ds).construct_graph_object()
+    g = MOTGraph.from_tensors(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': w.fps}, ds).construct_graph_object()
     ident = w.ident.to(dev)
     labels = (ident[g.edge_index[0]] == ident[g.edge_index[1]]).float()
     lib = _cabi.lib()

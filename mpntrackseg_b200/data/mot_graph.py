@@ -83,24 +83,80 @@ def _col(table, name, dev):
 class MOTGraph(object):
     """Edge construction + Graph assembly for one frame window.
 
-    graph_df: detection table (DataFrame or dict of arrays) with columns frame, bb_height,
-    bb_width, feet_x, feet_y, rows sorted by (frame, detection_id) (mot_graph.py:145).
-    reid_embeddings [N,256], node_core_feats [N,2048,8,4], node_ext_feats [N,256,14,14]: what
-    ``_load_appearance_data`` returns in the reference (mot_graph.py:153-193).
+    ``MOTGraph(seq_det_df, start_frame, end_frame, ensure_end_is_in, step_size, seq_info_dict, dataset_params,
+    inference_mode, max_frame_dist)`` is the reference's constructor (data/mot_graph.py:94-106): the window's rows are
+    selected from the sequence table (``_construct_graph_df``, :108-147) and the appearance tensors are loaded from
+    the per-frame embedding store (``_load_appearance_data``, :153-193) when the graph is built.
+    ``MOTGraph.from_tensors(graph_df, reid, node_core, node_ext, ...)`` takes an already selected table (DataFrame
+    or dict of arrays with columns frame, bb_height, bb_width, feet_x, feet_y, rows sorted by (frame, detection id))
+    and already loaded tensors ``reid [N,256]``, ``node_core [N,2048,8,4]`` (or pooled), ``node_ext [N,256,14,14]``.
     """
 
-    def __init__(self, graph_df, reid_embeddings, node_core_feats, node_ext_feats=None, seq_info_dict=None,
-                 dataset_params=None, inference_mode=False, max_frame_dist=None):
-        self.graph_df = graph_df
-        self.seq_info_dict = seq_info_dict or {}
+    def __init__(self, seq_det_df=None, start_frame=None, end_frame=None, ensure_end_is_in=False, step_size=None,
+                 seq_info_dict=None, dataset_params=None, inference_mode=False, max_frame_dist=None):
         self.dataset_params = dataset_params
+        self.step_size = step_size
+        self.seq_info_dict = seq_info_dict or {}
         self.inference_mode = inference_mode
-        self.max_frame_dist = max_frame_dist if max_frame_dist is not None else dataset_params['max_frame_dist']
+        self.max_frame_dist = max_frame_dist if max_frame_dist is not None or dataset_params is None \
+            else dataset_params['max_frame_dist']
         self.device = torch.device('cuda')
+        self.reid_embeddings = self.node_core_feats = self.node_ext_feats = None
+        self.graph_obj = None
+        if seq_det_df is not None:
+            self.graph_df, self.frames = self._construct_graph_df(seq_det_df=seq_det_df.copy(), start_frame=start_frame,
+                                                                  end_frame=end_frame, ensure_end_is_in=ensure_end_is_in)
+
+    @classmethod
+    def from_tensors(cls, graph_df, reid_embeddings, node_core_feats, node_ext_feats=None, seq_info_dict=None,
+                     dataset_params=None, inference_mode=False, max_frame_dist=None):
+        self = cls(seq_info_dict=seq_info_dict, dataset_params=dataset_params, inference_mode=inference_mode,
+                   max_frame_dist=max_frame_dist)
+        self.graph_df = graph_df
         self.reid_embeddings = reid_embeddings.to(self.device, torch.float32)
         self.node_core_feats = node_core_feats
         self.node_ext_feats = node_ext_feats
-        self.graph_obj = None
+        return self
+
+    def _construct_graph_df(self, seq_det_df, start_frame, end_frame=None, ensure_end_is_in=False):
+        """Frames of the window and its rows of the sequence table, sorted by (frame, detection_id).
+        reference: data/mot_graph.py:108-147"""
+        if end_frame is not None:
+            valid_frames = np.arange(start_frame, end_frame + 1, self.step_size)
+            if ensure_end_is_in and (end_frame not in valid_frames):
+                valid_frames = valid_frames.tolist() + [end_frame]
+        else:
+            valid_frames = np.arange(start_frame, seq_det_df.frame.max(), self.step_size)
+            if self.dataset_params['frames_per_graph'] != 'max':
+                valid_frames = valid_frames[:self.dataset_params['frames_per_graph']]
+            if self.dataset_params['max_detects'] is not None:
+                scene_df_ = seq_det_df[seq_det_df.frame.isin(valid_frames)].copy()
+                frames_cumsum = scene_df_.groupby('frame')['bb_left'].count().cumsum()
+                valid_frames = frames_cumsum[frames_cumsum <= self.dataset_params['max_detects']].index
+        graph_df = seq_det_df[seq_det_df.frame.isin(valid_frames)].copy()
+        graph_df = graph_df.sort_values(by=['frame', 'detection_id']).reset_index(drop=True)
+        return graph_df, sorted(graph_df.frame.unique())
+
+    def _load_appearance_data(self):
+        """(reid, node_core, node_ext) of the window's detections from the embedding store; with
+        ``dataset_params['node_core_pooled'] = True`` the pooled ``[N,2048]`` variant written by
+        ``EmbeddingStore.pool`` is read instead of the ``[N,2048,8,4]`` maps.  reference: data/mot_graph.py:153-193"""
+        import os.path as osp
+        from .embedding_store import load_precomputed_embeddings
+        dp = self.dataset_params
+        emb_dir = osp.join('embeddings', self.seq_info_dict['det_file_name'])
+        load = lambda d, dim: load_precomputed_embeddings(det_df=self.graph_df, seq_info_dict=self.seq_info_dict,
+                                                          embeddings_dir=osp.join(emb_dir, d), use_cuda=True,
+                                                          embedding_dim=dim, pin_memory=True)
+        reid = load(dp['reid_embeddings_dir'], '1D')
+        if dp['reid_embeddings_dir'] == dp['node_core_embeddings_dir']:
+            core = reid.clone()
+        elif dp.get('node_core_pooled', False):
+            core = load(dp['node_core_embeddings_dir'] + '_pooled', '1D')
+        else:
+            core = load(dp['node_core_embeddings_dir'], '3D')
+        ext = load(dp['node_ext_embeddings_dir'], '3D') if dp.get('node_ext_embeddings_dir') else None
+        return reid, core, ext
 
     def _get_edge_ixs(self, reid_embeddings):
         """Time-valid pairs, pruned to reciprocal top-k ReID neighbours in training mode.
@@ -121,6 +177,8 @@ class MOTGraph(object):
     def construct_graph_object(self):
         """reference: data/mot_graph.py:283-316"""
         dev = self.device
+        if self.reid_embeddings is None:
+            self.reid_embeddings, self.node_core_feats, self.node_ext_feats = self._load_appearance_data()
         pairs, dist = self._get_edge_ixs(self.reid_embeddings)
         if dist is None:
             dist = ops.pair_reid_dist(self.reid_embeddings, pairs)

@@ -301,6 +301,53 @@ def run_tracker_sequence_case():
                         input_checksum=gold_w['input_checksum'], param_checksum=gold_w['param_checksum'])
 
 
+def _reference_function(path, name, glob):
+    """Compile ONE function of a reference module that cannot be imported here (its module imports packages that
+    are absent) straight from the reference's source file; nothing is copied into the repo."""
+    import ast
+    src = open(path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = compile(ast.Module(body=[fn], type_ignores=[]), path, 'exec')
+    exec(code, glob)
+    return glob[name]
+
+
+def run_embedding_store_case():
+    """Per-frame embedding files in the layout the reference's preprocessing writes, read back by the reference's
+    own ``load_precomputed_embeddings`` (utils/rgb.py:150-188; utils/rgb.py itself needs skimage / pycocotools, so
+    the function is compiled from the file).  Store layout restated from seq_processor.py:445-446,462-472."""
+    import os.path as osp
+    import tempfile
+    loader = _reference_function('/root/reference/src/mot_neural_solver/utils/rgb.py', 'load_precomputed_embeddings',
+                                 {'osp': osp, 'np': np, 'torch': torch})
+    g = torch.Generator().manual_seed(31)
+    frames = np.array([4, 4, 4, 5, 5, 7, 7, 7, 7], dtype=np.int64)
+    det_ids = np.array([10, 11, 12, 13, 14, 15, 16, 17, 18], dtype=np.int64)
+    reid = torch.randn(9, 8, generator=g)
+    core = torch.randn(9, 6, 8, 4, generator=g)
+    tmp = tempfile.mkdtemp()
+    seq_info = {'seq_path': tmp, 'det_file_name': 'det'}
+    reid_t = torch.cat((torch.from_numpy(det_ids).view(-1, 1).float(), reid), dim=1)                       # :446
+    core_t = torch.cat((torch.from_numpy(det_ids).view(-1, 1, 1, 1).float().expand(-1, -1, 8, 4), core), dim=1)   # :445
+    for name, t in (('reid', reid_t), ('core', core_t)):
+        d = osp.join(tmp, 'processed_data', 'embeddings', 'det', name)
+        os.makedirs(d)
+        for f in np.unique(frames):                                                                        # :462-472
+            torch.save(t[torch.from_numpy(frames == f)], osp.join(d, f'{f}.pt'))
+    keep = np.array([0, 2, 3, 5, 6, 8])                       # the window's table: frames 4, 5, 7 with some detections filtered
+    df = pd.DataFrame({'frame': frames[keep], 'detection_id': det_ids[keep]})
+    out_reid = loader(det_df=df, seq_info_dict=seq_info, embeddings_dir=osp.join('embeddings', 'det', 'reid'), use_cuda=False)
+    out_core = loader(det_df=df, seq_info_dict=seq_info, embeddings_dir=osp.join('embeddings', 'det', 'core'), use_cuda=False,
+                      embedding_dim='3D')
+    sub = df[df.frame != 5]
+    out_sub = loader(det_df=sub, seq_info_dict=seq_info, embeddings_dir=osp.join('embeddings', 'det', 'reid'), use_cuda=False)
+    np.savez_compressed(os.path.join(HERE, 'embedding_store.npz'), frames=frames, det_ids=det_ids, reid=reid.numpy(),
+                        core=core.numpy(), keep=keep, out_reid=out_reid.numpy(), out_core=out_core.numpy(),
+                        out_sub=out_sub.numpy(), file_reid_5=torch.load(osp.join(tmp, 'processed_data', 'embeddings', 'det', 'reid', '5.pt')).numpy(),
+                        file_core_7=torch.load(osp.join(tmp, 'processed_data', 'embeddings', 'det', 'core', '7.pt')).numpy())
+    print('embedding_store', tuple(out_reid.shape), tuple(out_core.shape), tuple(out_sub.shape))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count() or 1)
     only = sys.argv[1:]
@@ -313,3 +360,5 @@ if __name__ == '__main__':
         run_tracker_sequence_case()
     if not only or 'edge_labels' in only:
         run_edge_labels_case()
+    if not only or 'embedding_store' in only:
+        run_embedding_store_case()

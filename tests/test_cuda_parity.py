@@ -79,7 +79,7 @@ def test_motgraph_matches_reference_golden(name):
     from mpntrackseg_b200.data.mot_graph import MOTGraph
     c = load_case(name)
     win, gold = c['win'], c['gold']
-    g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, c['ds'],
+    g = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, c['ds'],
                  inference_mode=False, max_frame_dist=c['max_frame_dist']).construct_graph_object()
     assert g.edge_index.dtype == torch.int64 and g.edge_index.is_cuda
     assert np.array_equal(g.edge_index.cpu().numpy(), gold['edge_index'].astype(np.int64)), 'KNN edge set'
@@ -133,7 +133,7 @@ def test_tracker_window_prune_and_predict():
     from mpntrackseg_b200.utils.graph import get_knn_mask
     c = load_case('tracker_window')
     win, gold, ds = c['win'], c['gold'], c['ds']
-    full = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
+    full = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
                     max_frame_dist=ds['frames_per_graph'] - 1).construct_graph_object()
     assert np.array_equal(full.edge_index.cpu().numpy(), gold['full_edge_index'].astype(np.int64))
     np.testing.assert_allclose(full.reid_emb_dists.cpu().numpy(), gold['full_dists'], rtol=3e-6)
@@ -175,7 +175,7 @@ def test_assign_edge_labels_against_golden():
     perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1)).to(dev())
     c = load_case('config1')
     cols = dict(synth.det_columns(c['win']), id=gold['ids'])
-    mg = MOTGraph(cols, c['win'].reid, c['win'].x, None, {'fps': c['win'].fps}, dict(c['ds'], true_edge_labels='closest'))
+    mg = MOTGraph.from_tensors(cols, c['win'].reid, c['win'].x, None, {'fps': c['win'].fps}, dict(c['ds'], true_edge_labels='closest'))
     mg.graph_obj = Graph(x=c['win'].x, edge_index=ei[:, perm].contiguous())
     assert np.array_equal(mg.assign_edge_labels().cpu().numpy(), gold['labels_closest'][perm.cpu().numpy()])
     with pytest.raises(ValueError):
@@ -189,7 +189,7 @@ class _FullGraph(object):
 def _sequence_full_graph(c, with_tables=True):
     from mpntrackseg_b200.data.mot_graph import MOTGraph
     win, ds = c['win'], c['ds']
-    mg = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
+    mg = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds, inference_mode=True,
                   max_frame_dist=ds['frames_per_graph'] - 1)
     mg.construct_graph_object()
     if with_tables:                                            # the MOTGraph itself: detection table + embeddings available
@@ -411,7 +411,7 @@ def test_config2_scale_against_oracle(engine):
     ref_g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds)
     with torch.no_grad():
         ref = mpn_ref.mpn_forward(P, mp, win.x, ref_g['edge_index'], ref_g['edge_attr'])
-    g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
+    g = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
     assert torch.equal(g.edge_index.cpu(), ref_g['edge_index'])
     model = make_model(mp, P, engine)
     with torch.no_grad():
@@ -462,7 +462,7 @@ def test_tc_engine_scales_activations_beyond_the_fp16_range():
     with torch.no_grad():
         ref = mpn_ref.mpn_forward(P, mp, win.x, ref_g['edge_index'], ref_g['edge_attr'], return_state=True)
     assert float(ref['node_state'].max()) > 10 * 65504.0, 'the case must exceed the fp16 range by 10x'
-    g = MOTGraph(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
+    g = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
     assert torch.equal(g.edge_index.cpu(), ref_g['edge_index'])
     model = make_model(mp, P, 'tc')
     got, x_state = _core_states(model, g)
@@ -570,7 +570,7 @@ def test_single_frame_and_single_node_windows_build_empty_graphs():
         n = len(frames)
         cols = {'frame': np.asarray(frames, dtype=np.float64), 'bb_height': np.full(n, 100.0), 'bb_width': np.full(n, 40.0),
                 'feet_x': np.arange(n, dtype=np.float64), 'feet_y': np.zeros(n)}
-        g = MOTGraph(cols, torch.randn(n, 256), torch.randn(n, 2048, 1, 1).to(dev()), None, {'fps': 30.0}, ds).construct_graph_object()
+        g = MOTGraph.from_tensors(cols, torch.randn(n, 256), torch.randn(n, 2048, 1, 1).to(dev()), None, {'fps': 30.0}, ds).construct_graph_object()
         assert tuple(g.edge_index.shape) == (2, 0) and g.edge_attr.shape[0] == 0
 
 
@@ -595,7 +595,7 @@ def test_batched_graph_build_and_forward_match_per_window_path():
             gg = batch.graph(g)
             assert torch.equal(gg.edge_index.cpu(), ref_g['edge_index']), (g, recip)
             np.testing.assert_allclose(gg.edge_attr.cpu().numpy(), ref_g['edge_attr'].numpy(), rtol=3e-6, atol=1e-6)
-            single = MOTGraph(synth.det_columns(w), w.reid, w.x, None, {'fps': 30.0}, ds,
+            single = MOTGraph.from_tensors(synth.det_columns(w), w.reid, w.x, None, {'fps': 30.0}, ds,
                               max_frame_dist=mfd).construct_graph_object()
             assert torch.equal(single.edge_index, gg.edge_index)
             with torch.no_grad():
@@ -856,3 +856,48 @@ def test_adam_step_matches_torch_adam():
         tr.adam_step()
     for rp, p in zip(ref_p, tr.named.values()):
         np.testing.assert_allclose(p.detach().cpu().numpy(), rp.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_embedding_store_pool_and_motgraph_from_store(tmp_path):
+    """f3: a store in the reference's layout -> pooled variant -> MOTGraph(seq_det_df, start_frame, end_frame, ...)
+    builds the same graph / logits as the tensor-taking form; SequenceEmbeddings slices are the window's rows."""
+    import pandas as pd
+    from mpntrackseg_b200 import ops
+    from mpntrackseg_b200.data.embedding_store import EmbeddingStore, SequenceEmbeddings
+    from mpntrackseg_b200.data.mot_graph import MOTGraph
+    win = synth.make_window(T=8, D=9, k=6, seed=41, node_feats='full')
+    cols = synth.det_columns(win)
+    df = pd.DataFrame(dict(cols, frame=win.frame.numpy(), detection_id=np.arange(win.N), bb_left=np.zeros(win.N)))
+    seq_info = {'seq_path': str(tmp_path), 'det_file_name': 'det', 'fps': win.fps}
+    ds = dict(default_dataset_params(top_k_nns=6, frames_per_graph=5), reid_embeddings_dir='reid',
+              node_core_embeddings_dir='core', node_ext_embeddings_dir=None)
+    store = EmbeddingStore(seq_info)
+    store.write('reid', win.frame, df.detection_id.values, win.reid)
+    store.write('core', win.frame, df.detection_id.values, win.x)
+    store.pool('core', 'core_pooled', device=dev())
+    pooled_ref = ops.avgpool(win.x.to(dev())).cpu()
+    got = torch.cat([store.read_frame('core_pooled', f) for f in store.frames('core_pooled')])
+    assert torch.equal(got[:, 0], torch.arange(win.N, dtype=torch.float32)) and torch.equal(got[:, 1:], pooled_ref)
+    np.testing.assert_allclose(got[:, 1:].numpy(), win.x.mean(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-6)
+
+    seq = SequenceEmbeddings(df, seq_info, ds, pooled=True)
+    a, b = seq.rows(3, 7)
+    assert (a, b) == (2 * win.D, 7 * win.D) and seq.node_core.is_pinned()
+    reid_w, core_w = seq.window(3, 7, device=dev())
+    torch.cuda.synchronize()
+    assert torch.equal(reid_w.cpu(), win.reid[a:b]) and torch.equal(core_w.cpu(), pooled_ref[a:b])
+
+    mp = default_graph_model_params(4, 3)
+    P = synth.make_params(mp, seed=3, gain=2.0, core_only=True)
+    model = make_model(mp, P)
+    sel = slice(a, b)
+    tab = {k: v[sel] for k, v in cols.items()}
+    g_ref = MOTGraph.from_tensors(tab, win.reid[sel], win.x[sel].to(dev()), None, seq_info, ds).construct_graph_object()
+    for pooled_flag, exact in ((False, True), (True, True)):
+        mg = MOTGraph(seq_det_df=df, start_frame=3, end_frame=7, step_size=1, seq_info_dict=seq_info,
+                      dataset_params=dict(ds, node_core_pooled=pooled_flag))
+        g = mg.construct_graph_object()
+        assert torch.equal(g.edge_index, g_ref.edge_index) and torch.equal(g.edge_attr, g_ref.edge_attr)
+        with torch.no_grad():
+            a_, b_ = model(g)['classified_edges'][-1], model(g_ref)['classified_edges'][-1]
+        assert torch.equal(a_, b_) if exact else torch.allclose(a_, b_)

@@ -28,7 +28,7 @@ def t(fn, name, n=3):
     torch.cuda.synchronize(); print(f'{name}: {(time.perf_counter()-t0)/n*1e3:.2f} ms'); return r
 
 inputs = t(lambda: [{k: v.to(dev, non_blocking=True) for k, v in h.items()} for h in host], 'h2d')
-graphs = t(lambda: [MOTGraph(d, d['reid'], d['x'], None, {'fps': 30.0}, ds).construct_graph_object() for d in inputs], 'graph build')
+graphs = t(lambda: [MOTGraph.from_tensors(d, d['reid'], d['x'], None, {'fps': 30.0}, ds).construct_graph_object() for d in inputs], 'graph build')
 with torch.no_grad():
     x0 = t(lambda: [model.encode_nodes(g.x) for g in graphs], 'encode nodes')
     outs = t(lambda: model.forward_batch(graphs), 'forward_batch')

@@ -14,7 +14,7 @@ model = MOTMPNet(mp).to(dev).eval(); model.load_state_dict(P, strict=False); mod
 graphs = []
 for g in range(G):
     w = synth.make_window(T=15, D=150, k=50, seed=g)
-    graphs.append(MOTGraph(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': 30.0}, ds).construct_graph_object())
+    graphs.append(MOTGraph.from_tensors(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': 30.0}, ds).construct_graph_object())
 buf = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
 lib = _cabi.lib()
 lib.mpn_tc_set_trace.argtypes = [C.c_void_p]

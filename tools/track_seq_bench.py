@@ -26,7 +26,7 @@ class Full(object):
 
 
 def full_graph(win, ds):
-    mg = MOTGraph(synth.det_columns(win), win.reid, win.x.to(dev), None, {'fps': win.fps}, ds, inference_mode=True,
+    mg = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x.to(dev), None, {'fps': win.fps}, ds, inference_mode=True,
                   max_frame_dist=FPG - 1)
     mg.construct_graph_object()
     mg.frames = sorted(set(win.frame.tolist()))

@@ -24,7 +24,7 @@ P = synth.make_params(mp, seed=6, gain=0.95, core_only=True)
 
 def window(seed):
     w = synth.make_window(T=20, D=8, k=100, seed=seed)
-    g = MOTGraph(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': 30.0}, ds).construct_graph_object()
+    g = MOTGraph.from_tensors(synth.det_columns(w), w.reid, w.x.to(dev), None, {'fps': 30.0}, ds).construct_graph_object()
     ident = w.ident.to(dev)
     return g, (ident[g.edge_index[0]] == ident[g.edge_index[1]]).float()
 
