@@ -230,6 +230,8 @@ def run_b200(a):
     # sequence's graph_df) + one node-feature tensor per window
     cols = {k: torch.cat([torch.from_numpy(synth.det_columns(w)[k]) for w in wins])
             for k in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
+    for g in range(len(wins)):                      # one table for the job: window g owns its own frame numbers
+        cols['frame'][node_ptr[g]:node_ptr[g + 1]] += g * (a.frames + 1)
     cols['reid'] = torch.cat([w.reid for w in wins])
     host = {k: v.pin_memory() for k, v in cols.items()}
     devin = {k: v.to(dev) for k, v in host.items()}
@@ -303,8 +305,6 @@ def run_b200(a):
     store = EmbeddingStore(seq_info)
     n_tot = node_ptr[-1]
     table = {k: cols[k].numpy().copy() for k in ('frame', 'bb_height', 'bb_width', 'feet_x', 'feet_y')}
-    for g in range(len(wins)):                                        # one table for the job: window g owns its own frames
-        table['frame'][node_ptr[g]:node_ptr[g + 1]] += g * (a.frames + 1)
     table['detection_id'] = np.arange(n_tot, dtype=np.int64)
     det_df = pd.DataFrame(table)
     store.write('reid', table['frame'], table['detection_id'], cols['reid'])
@@ -406,6 +406,7 @@ def run_b200(a):
     with torch.no_grad():
         ref_last = step(devin)[1].logits[-1].cpu()
     e2e_max_diff = float((res - ref_last).abs().max())
+    assert e2e_max_diff == 0.0, f'store arm and device-resident arm disagree by {e2e_max_diff}'
 
     # ---- second number: raw [N,2048,8,4] maps from pinned memory every step (the round-1 e2e definition)
     raw_steps = min(a.steps, 5)

@@ -52,15 +52,68 @@ constexpr int OFF_F32 = OFF_L4L + L4_KS * L4_SLAB;          // fp32 tail
 constexpr int F_B1 = 0, F_FB0 = F_B1 + DE, F_FB1 = F_FB0 + FHP, F_CW0 = F_FB1 + DN, F_CB0 = F_CW0 + DE * CH,
               F_CW1 = F_CB0 + CH, F_CB1 = F_CW1 + CH, F_COUNT = F_CB1 + 4;
 constexpr int IMG_BYTES = (OFF_F32 + F_COUNT * 4 + 127) / 128 * 128;
+// ---- weight image of the node kernel: node Linear 64 -> 32 (K steps 0..3) and the hoisted row term 32 -> 80 (K steps 0..1)
+constexpr int NW_KS = 4, NW_SLAB = DN * 32;
+constexpr int PW_KS = 2, PW_SLAB = EH * 32;
+constexpr int NOFF_NWH = 0, NOFF_NWL = NOFF_NWH + NW_KS * NW_SLAB;
+constexpr int NOFF_PWH = NOFF_NWL + NW_KS * NW_SLAB, NOFF_PWL = NOFF_PWH + PW_KS * PW_SLAB;
+constexpr int NOFF_F32 = NOFF_PWL + PW_KS * PW_SLAB;       // bn[32]
+constexpr int NIMG_BYTES = (NOFF_F32 + DN * 4 + 127) / 128 * 128;
 
 __device__ __forceinline__ int slab_off(int n, int k16) {           // byte offset inside a slab
   return (n >> 3) * 256 + (k16 >> 3) * 128 + (n & 7) * 16 + (k16 & 7) * 2;
 }
 
+// =================================================================== range bookkeeping
+// Per forward: sched[t] = s_t (exponent of the step's scale), amax[t] = float bits of the largest true activation
+// the edge kernel of step t saw, xmax[t] = largest |x_lat| consumed by step t (t = 1..num_steps; all zeroed at start).
+constexpr int MAX_STEPS = 1000;
+// The lifted low halves keep 22 bits for any operand whose high half is a normal fp16 number (>= 2^-14), so the scale
+// can leave generous headroom at no cost in precision: the lagged maximum is brought to <= 2^6 (1024x headroom for the
+// growth of one step); values down to 2^-20 of the maximum still have all their bits.
+constexpr float SCALE_TARGET = 64.f;
+constexpr int INIT_SHIFT = 8;                // the constant x_init / e_init rows are stored x 2^-8, their weight slabs carry 2^(8 - s_t):
+                                             // the slabs stay normal fp16 numbers for s_t up to 22 (values up to ~2.7e8)
+constexpr int FLOW_SHIFT = 7;                // a flow vector sums up to ~100 messages: operand scale 2^-(s_t + 7)
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }   // 2^e, |e| <= 126
+// s_{t+1} from what is known when the node kernel of step t starts: the edge kernel's activation maximum of step t
+// and the node-state maxima of steps t and t-1 (their ratio predicts the growth of the state being produced).
+__device__ __forceinline__ int scale_for(float a_t, float x_t, float x_tm1, float target) {
+  float growth = x_tm1 > 0.f ? x_t / x_tm1 : 4.f;
+  growth = fminf(fmaxf(growth, 1.f), 64.f);
+  const float lag = fmaxf(a_t, x_t * growth);
+  if (!(lag > target)) return 0;
+  int e;
+  frexpf(lag / target, &e);             // lag / target = m * 2^e, m in [0.5, 1)
+  return e > 100 ? 100 : e;
+}
+__device__ __forceinline__ void atomic_max_f32(uint32_t* addr, float v) {   // v >= 0: integer order = float order
+  const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(addr, m);
+}
+
 // =================================================================== weight packing (once per forward)
 // One image per direction (flow_out / flow_in); layers 1-2 and the classifier are shared.
 __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ img_out, uint8_t* __restrict__ img_in,
-                                    int cls_in_l3) {
+                                    uint8_t* __restrict__ img_node, int cls_in_l3, int32_t* __restrict__ status) {
+  int bad = 0;                       // a weight whose fp16 image (x 2^INIT_SHIFT for the constant-row slabs) is not finite
+  auto fits = [&](float v) { if (!(fabsf(v) * pow2i(INIT_SHIFT) < 65000.f)) bad = 1; };
+  {
+    auto putn = [&](int off_h, int off_l, int slab_bytes, int n, int k, float v) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
+      const int o = (k >> 4) * slab_bytes + slab_off(n, k & 15);
+      *reinterpret_cast<__half*>(img_node + off_h + o) = h;
+      *reinterpret_cast<__half*>(img_node + off_l + o) = l;
+    };
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < DN * 2 * DN; i += nt) { fits(w.node_w[i]); putn(NOFF_NWH, NOFF_NWL, NW_SLAB, i / (2 * DN), i % (2 * DN), w.node_w[i]); }
+    for (int i = tid; i < EH * DN; i += nt) {            // edge layer 0, input columns 32..63 (x_lat[row])
+      const int n = i / DN, k = i % DN;
+      putn(NOFF_PWH, NOFF_PWL, PW_SLAB, n, k, w.edge_w0[n * 160 + 32 + k]);
+    }
+    for (int i = tid; i < DN; i += nt) reinterpret_cast<float*>(img_node + NOFF_F32)[i] = w.node_b[i];
+  }
   for (int dir = 0; dir < 2; ++dir) {
     uint8_t* img = dir == 0 ? img_out : img_in;
     const float* f0 = dir == 0 ? w.fout_w0 : w.fin_w0;
@@ -68,6 +121,7 @@ __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ im
     const float* fb0 = dir == 0 ? w.fout_b0 : w.fin_b0;
     const float* fb1 = dir == 0 ? w.fout_b1 : w.fin_b1;
     auto put = [&](int off_h, int off_l, int slab_bytes, int n, int k, float v) {
+      fits(v);
       const __half h = __float2half_rn(v);
       const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
       const int o = (k >> 4) * slab_bytes + slab_off(n, k & 15);
@@ -108,28 +162,7 @@ __global__ void pack_weights_kernel(mpn_core_weights w, uint8_t* __restrict__ im
       ft[i] = v;
     }
   }
-}
-
-// =================================================================== range bookkeeping
-// Per forward: sched[t] = s_t (exponent of the step's scale), amax[t] = float bits of the largest true activation
-// the edge kernel of step t saw, xmax[t] = largest |x_lat| consumed by step t (t = 1..num_steps; all zeroed at start).
-constexpr int MAX_STEPS = 1000;
-constexpr float SCALE_TARGET = 1024.f;      // lagged maximum is brought to <= 2^10: 64x headroom to the fp16 range
-__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }   // 2^e, |e| <= 126
-// s_{t+1} from what is known when the node kernel of step t starts: the edge kernel's activation maximum of step t
-// and the node-state maxima of steps t and t-1 (their ratio predicts the growth of the state being produced).
-__device__ __forceinline__ int scale_for(float a_t, float x_t, float x_tm1) {
-  float growth = x_tm1 > 0.f ? x_t / x_tm1 : 4.f;
-  growth = fminf(fmaxf(growth, 1.f), 64.f);
-  const float lag = fmaxf(a_t, x_t * growth);
-  if (!(lag > SCALE_TARGET)) return 0;
-  int e;
-  frexpf(lag / SCALE_TARGET, &e);             // lag / target = m * 2^e, m in [0.5, 1)
-  return e > 100 ? 100 : e;
-}
-__device__ __forceinline__ void atomic_max_f32(uint32_t* addr, float v) {   // v >= 0: integer order = float order
-  const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
-  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(addr, m);
+  if (bad) atomicOr(status, 1);
 }
 
 // =================================================================== node-side kernels
@@ -164,7 +197,7 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
   for (int64_t r = warp; r < n; r += nwarps) {
     const float v = x_init[r * DN + lane];
     mx = fmaxf(mx, fabsf(v));
-    store_split_row(xi + r * 64, lane, v, &ovf);
+    store_split_row(xi + r * 64, lane, v * pow2i(-INIT_SHIFT), &ovf);
     store_split_row(xl0 + r * 64, lane, v, &ovf);
     float a0[3], a1[3];
 #pragma unroll
@@ -190,7 +223,24 @@ __global__ void __launch_bounds__(256) prep_nodes_kernel(const float* __restrict
 
 // Per step: x' = ReLU(Wn [flow_in | flow_out] + bn)  (models/mpn.py:97-99), then the split copy of
 // x' for the next step's gathers and prow[r] = pinit[r] + W0[:, 32:64] x'.
-__global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
+//
+// A warp takes NODE_NB = 8 consecutive nodes at a time, lane = output feature.  The 8 nodes' input vectors sit in a
+// per-warp shared-memory tile [input][node] and are read back as 16-byte broadcasts, so every weight (node Linear: in
+// registers; prow: one shared-memory load) is used for 8 nodes, and the products run as packed FFMA2 (two nodes per
+// instruction, the weight as the scalar operand): ~120 instructions per node instead of ~300 with a node per warp.
+constexpr int NODE_NB = 4;
+__device__ __forceinline__ float2 ffma2(float2 a, float w, float2 c) {
+  unsigned long long ra, rw, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rw) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rw), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 3) node_tc_kernel(const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr,
                                                          int64_t num_nodes, int64_t num_out, int32_t chunks_out,
                                                          int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
                                                          const float* __restrict__ node_w, const float* __restrict__ node_b,
@@ -198,137 +248,381 @@ __global__ void __launch_bounds__(256, 2) node_tc_kernel(const int32_t* __restri
                                                          __half* __restrict__ xl_next, float* __restrict__ prow,
                                                          float* __restrict__ x_out, int32_t step, int32_t* __restrict__ sched,
                                                          const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax,
-                                                         int32_t* __restrict__ status) {
-  // Warp per node, lane = output feature.  The lane's column of the node Linear lives in REGISTERS (64 values); a
-  // node's input vector is staged in a per-warp shared-memory buffer and read back as 16-byte broadcasts, so a node
-  // costs ~120 shared-memory instructions instead of 96 shuffles + 160 loads.  The next node's inputs are loaded while the
-  // current one is computed (its row pointers one node earlier), which hides the dependent global round trips.
-  __shared__ float s_wn[2 * DN * DN];   // [in][out]
-  __shared__ float s_bn[DN];
-  __shared__ float s_w0[DN * EH];       // [i][o] over W0 columns 32..63
-  __shared__ __align__(16) float s_vec[8][96];
-  for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
-    const int o = idx / (2 * DN), i = idx - o * 2 * DN;
-    s_wn[i * DN + o] = node_w[idx];
-  }
-  for (int o = threadIdx.x; o < DN; o += blockDim.x) s_bn[o] = node_b[o];
+                                                         float scale_target, int32_t* __restrict__ status) {
+  __shared__ float s_w0[DN * EH];                                   // [i][o] over W0 columns 32..63
+  __shared__ float s_wn[2 * DN * DN];                               // node Linear, [in][out]
+  __shared__ __align__(16) float s_in[8][2 * DN][NODE_NB];          // per warp: [input feature][node]
+  __shared__ __align__(16) float s_x[8][DN][NODE_NB];               // per warp: x' [feature][node]
   for (int idx = threadIdx.x; idx < EH * DN; idx += blockDim.x) {
     const int o = idx / DN, i = idx - o * DN;
     s_w0[i * EH + o] = w0[o * 160 + 32 + i];
   }
+  for (int idx = threadIdx.x; idx < 2 * DN * DN; idx += blockDim.x) {
+    const int o = idx / (2 * DN), i = idx - o * 2 * DN;
+    s_wn[i * DN + o] = node_w[idx];
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const float bn = node_b[lane];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float wn[2 * DN];
-#pragma unroll
-  for (int i = 0; i < 2 * DN; ++i) wn[i] = s_wn[i * DN + lane];
-  const int o2 = lane + 64 < EH ? lane + 64 : lane;                    // lanes >= 16 have no third output (result unused)
-  const float bn = s_bn[lane];
-  float* vec = s_vec[threadIdx.x >> 5];
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int o2 = lane + 64 < EH ? lane + 64 : lane;                  // lanes >= 16 have no third output (result unused)
   int ovf = 0;
   // scale of the step that will consume this kernel's outputs (x_lat rows and prow are written pre-scaled)
   const int s_next = scale_for(__uint_as_float(amax[step]), __uint_as_float(xmax[step]),
-                               step > 1 ? __uint_as_float(xmax[step - 1]) : 0.f);
+                               step > 1 ? __uint_as_float(xmax[step - 1]) : 0.f, scale_target);
   const float sig_next = pow2i(-s_next);
   if (blockIdx.x == 0 && threadIdx.x == 0) sched[step + 1] = s_next;
   float mx = 0.f;
 
-  auto load_ptrs = [&](int64_t r, int32_t* p) { p[0] = in_ptr[r]; p[1] = in_ptr[r + 1]; p[2] = out_ptr[r]; p[3] = out_ptr[r + 1]; };
-  // one direction's flow vector: the row sum written by the edge kernel, or its partials combined in fixed order
-  auto load_flow = [&](int64_t r, int d, int64_t s0, int64_t s1) {
+  // One direction's flow vector of a node: the row sum written by the edge kernel (row inside one 16-slot granule), or
+  // its granule partials added in granule order.  Branch-free: every piece is an unconditional load from a valid
+  // address (masked to 0 when absent), so the loads of all nodes of the group are in flight together; only rows that
+  // span more than four granules (degree > 48) take the loop.
+  struct FlowReq { float v0, v1, v2, v3; int64_t ca, cb; };
+  const int64_t gmask = ((int64_t)1 << chunk_shift) - 1;
+  auto issue_flow = [&](int64_t r, int d, int64_t s0, int64_t s1, bool live) {
     const int64_t seg_base = d == 0 ? num_out : 0;
     const int64_t chunk_off = d == 0 ? chunks_out : 0;
-    float v = 0.f;
-    if (s1 > s0) {
-      const int64_t ca = (s0 - seg_base) >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
-      if (ca == cb) {
-        v = flow[r * 2 * DN + d * DN + lane];
-      } else {
-        const bool first_in_chunk = ((s0 - seg_base) & ((1 << chunk_shift) - 1)) == 0;
-        // the partials of up to four granules are loaded together (independent loads), then added in granule order
-        const int more = (int)(cb - ca);
-        const float* pp = part + ((chunk_off + ca + 1) * 2) * DN + lane;
-        const float v0 = part[((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN + lane];
-        const float v1 = pp[0];
-        const float v2 = more >= 2 ? pp[2 * DN] : 0.f;
-        const float v3 = more >= 3 ? pp[4 * DN] : 0.f;
-        v = v0 + v1;
-        if (more >= 2) v += v2;
-        if (more >= 3) v += v3;
-        for (int64_t t = ca + 4; t <= cb; ++t) v += part[((chunk_off + t) * 2) * DN + lane];
-      }
-    }
+    const bool has = live && s1 > s0;
+    const int64_t rel0 = s0 - seg_base;
+    const int64_t ca = rel0 >> chunk_shift, cb = has ? (s1 - 1 - seg_base) >> chunk_shift : ca;
+    const int64_t more = cb - ca;
+    const bool single = more == 0;
+    const bool first_in_chunk = (rel0 & gmask) == 0;
+    const float* p0 = single ? flow + r * 2 * DN + d * DN : part + ((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN;
+    const float* pp = part + ((chunk_off + ca + 1) * 2) * DN;
+    FlowReq q;
+    q.v0 = (has ? p0 : flow)[lane];
+    q.v1 = (has && more >= 1 ? pp : flow)[lane];
+    q.v2 = (has && more >= 2 ? pp + 2 * DN : flow)[lane];
+    q.v3 = (has && more >= 3 ? pp + 4 * DN : flow)[lane];
+    q.v0 = has ? q.v0 : 0.f;
+    q.v1 = has && more >= 1 ? q.v1 : 0.f;
+    q.v2 = has && more >= 2 ? q.v2 : 0.f;
+    q.v3 = has && more >= 3 ? q.v3 : 0.f;
+    q.ca = chunk_off + ca; q.cb = chunk_off + cb;
+    return q;
+  };
+  auto finish_flow = [&](const FlowReq& q) {
+    float v = q.v0 + q.v1;                                              // + 0.f is exact: same sums as the piecewise form
+    v += q.v2;
+    v += q.v3;
+    for (int64_t t = q.ca + 4; t <= q.cb; ++t) v += part[(t * 2) * DN + lane];
     return v;
   };
-  auto load_inputs = [&](int64_t r, const int32_t* p, float* fl, float* pin) {
-    fl[0] = load_flow(r, 0, p[0], p[1]);                                // flow_in
-    fl[1] = load_flow(r, 1, p[2], p[3]);                                // flow_out
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { const int o = lane + 32 * q; pin[q] = o < EH ? pinit[r * EH + o] : 0.f; }
+  auto load_ptrs = [&](int64_t r0, int cnt) {
+    // row pointers of the group's nodes (+1): lanes 0..NB hold in_ptr, lanes 16..16+NB out_ptr
+    int32_t pv = 0;
+    if (r0 < num_nodes && (lane & 15) <= cnt) pv = lane < 16 ? in_ptr[r0 + lane] : out_ptr[r0 + lane - 16];
+    return pv;
   };
+  auto group_cnt = [&](int64_t r0) { return (int)(num_nodes - r0 < NODE_NB ? (num_nodes - r0 > 0 ? num_nodes - r0 : 0) : NODE_NB); };
 
-  int64_t r = warp;
-  float fl[2] = {0.f, 0.f}, pin[3] = {0.f, 0.f, 0.f};
-  int32_t pn[4] = {0, 0, 0, 0};
-  if (r < num_nodes) {
-    int32_t p[4];
-    load_ptrs(r, p);
-    load_inputs(r, p, fl, pin);
-    if (r + nwarps < num_nodes) load_ptrs(r + nwarps, pn);
-  }
-  for (; r < num_nodes; r += nwarps) {
-    const int64_t r1 = r + nwarps, r2 = r1 + nwarps;
-    float nfl[2] = {0.f, 0.f}, npin[3] = {0.f, 0.f, 0.f};
-    int32_t p2[4] = {0, 0, 0, 0};
-    if (r1 < num_nodes) load_inputs(r1, pn, nfl, npin);
-    if (r2 < num_nodes) load_ptrs(r2, p2);
-
-    vec[lane] = fl[0];
-    vec[DN + lane] = fl[1];
-    __syncwarp();
-    float acc = bn;
+  float (*vin)[NODE_NB] = s_in[wib];
+  float (*vx)[NODE_NB] = s_x[wib];
+  int32_t pv = load_ptrs(warp * NODE_NB, group_cnt(warp * NODE_NB));
+  for (int64_t r0 = warp * NODE_NB; r0 < num_nodes; r0 += nwarps * NODE_NB) {
+    const int cnt = group_cnt(r0);
+    FlowReq qi[NODE_NB], qo[NODE_NB];
 #pragma unroll
-    for (int i = 0; i < 2 * DN / 4; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(vec + 4 * i);
-      acc = fmaf(v.x, wn[4 * i], acc);
-      acc = fmaf(v.y, wn[4 * i + 1], acc);
-      acc = fmaf(v.z, wn[4 * i + 2], acc);
-      acc = fmaf(v.w, wn[4 * i + 3], acc);
+    for (int j = 0; j < NODE_NB; ++j) {
+      const int32_t i0 = __shfl_sync(0xffffffffu, pv, j), i1 = __shfl_sync(0xffffffffu, pv, j + 1);
+      const int32_t q0 = __shfl_sync(0xffffffffu, pv, 16 + j), q1 = __shfl_sync(0xffffffffu, pv, 17 + j);
+      qi[j] = issue_flow(r0 + j, 0, i0, i1, j < cnt);                   // flow_in
+      qo[j] = issue_flow(r0 + j, 1, q0, q1, j < cnt);                   // flow_out
     }
-    const float xn = fmaxf(acc, 0.f);
-    vec[2 * DN + lane] = xn;
+    // hoisted-term inputs of the group's nodes (independent loads, in flight with the flow pieces)
+    float2 pa[3][NODE_NB / 2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int o = q < 2 ? lane + 32 * q : o2;
+#pragma unroll
+      for (int j = 0; j < NODE_NB; j += 2) {
+        pa[q][j >> 1].x = pinit[(j < cnt ? r0 + j : 0) * EH + o];
+        pa[q][j >> 1].y = pinit[(j + 1 < cnt ? r0 + j + 1 : 0) * EH + o];
+      }
+    }
+    pv = load_ptrs(r0 + nwarps * NODE_NB, group_cnt(r0 + nwarps * NODE_NB));   // next group's pointers, one group ahead
+    float fi[NODE_NB], fo[NODE_NB];
+#pragma unroll
+    for (int j = 0; j < NODE_NB; ++j) { fi[j] = finish_flow(qi[j]); fo[j] = finish_flow(qo[j]); }
+    __syncwarp();                                                       // the previous group's reads of the tiles are done
+    *reinterpret_cast<float4*>(&vin[lane][0]) = make_float4(fi[0], fi[1], fi[2], fi[3]);
+    *reinterpret_cast<float4*>(&vin[DN + lane][0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
     __syncwarp();
-    if (x_out != nullptr) x_out[r * DN + lane] = xn;
-    mx = fmaxf(mx, xn);
-    store_split_row(xl_next + r * 64, lane, xn * sig_next, &ovf);
-    float a[3] = {pin[0], pin[1], pin[2]};
+    // ---- node Linear 64 -> 32 for the group's nodes
+    float2 acc[NODE_NB / 2];
 #pragma unroll
-    for (int i = 0; i < DN / 4; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(vec + 2 * DN + 4 * i);
-      const float* wr = s_w0 + 4 * i * EH;
-      const float xs[4] = {v.x, v.y, v.z, v.w};
+    for (int h = 0; h < NODE_NB / 2; ++h) acc[h] = make_float2(bn, bn);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a[0] = fmaf(xs[u], wr[u * EH + lane], a[0]);
-        a[1] = fmaf(xs[u], wr[u * EH + lane + 32], a[1]);
-        a[2] = fmaf(xs[u], wr[u * EH + o2], a[2]);
+    for (int i = 0; i < 2 * DN; ++i) {
+      const float4 va = *reinterpret_cast<const float4*>(&vin[i][0]);
+      const float w = s_wn[i * DN + lane];
+      acc[0] = ffma2(make_float2(va.x, va.y), w, acc[0]);
+      acc[1] = ffma2(make_float2(va.z, va.w), w, acc[1]);
+    }
+    float xn[NODE_NB];
+#pragma unroll
+    for (int h = 0; h < NODE_NB / 2; ++h) { xn[2 * h] = fmaxf(acc[h].x, 0.f); xn[2 * h + 1] = fmaxf(acc[h].y, 0.f); }
+    *reinterpret_cast<float4*>(&vx[lane][0]) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+#pragma unroll
+    for (int j = 0; j < NODE_NB; ++j) {
+      if (j < cnt) {
+        if (x_out != nullptr) x_out[(r0 + j) * DN + lane] = xn[j];
+        mx = fmaxf(mx, xn[j]);
+        store_split_row(xl_next + (r0 + j) * 64, lane, xn[j] * sig_next, &ovf);
+      }
+    }
+    __syncwarp();
+    // ---- prow = pinit + W0[:, 32:64] x' for the group's nodes (80 outputs: lane, lane + 32, lane + 64)
+#pragma unroll 8
+    for (int i = 0; i < DN; ++i) {
+      const float4 va = *reinterpret_cast<const float4*>(&vx[i][0]);
+      const float w_0 = s_w0[i * EH + lane], w_1 = s_w0[i * EH + lane + 32], w_2 = s_w0[i * EH + o2];
+      const float ws[3] = {w_0, w_1, w_2};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        pa[q][0] = ffma2(make_float2(va.x, va.y), ws[q], pa[q][0]);
+        pa[q][1] = ffma2(make_float2(va.z, va.w), ws[q], pa[q][1]);
       }
     }
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int o = lane + 32 * q;
-      if (o < EH) prow[r * EH + o] = a[q] * sig_next;
+      if (o < EH) {
+#pragma unroll
+        for (int j = 0; j < NODE_NB; j += 2) {
+          if (j < cnt) prow[(r0 + j) * EH + o] = pa[q][j >> 1].x * sig_next;
+          if (j + 1 < cnt) prow[(r0 + j + 1) * EH + o] = pa[q][j >> 1].y * sig_next;
+        }
+      }
     }
-    __syncwarp();                                                       // vec is rewritten by the next node
-    fl[0] = nfl[0]; fl[1] = nfl[1];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) pin[q] = npin[q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pn[q] = p2[q];
   }
   atomic_max_f32(xmax + step + 1, mx);
   if (ovf) atomicOr(status, 1);
+}
+
+// ---- the same node update on the tensor cores (default).  Tile = 128 nodes, TMEM lane = node = thread; two groups of
+// 4 warps per CTA, one tile in flight each.  A thread gathers its node's two flow vectors (the row sum, or the granule
+// partials added in granule order), splits them into the A operand in TMEM, the node Linear runs as 12 MMAs (N = 32),
+// the epilogue writes x' (fp32 on the last step, split rows in the next step's scale) and leaves the scaled split x'
+// in TMEM as the A operand of the hoisted row term (6 MMAs, N = 80), whose epilogue adds pinit and stores prow.
+constexpr int NT2_THREADS = 256;
+constexpr int N2_A1H = 0, N2_A1L = 32, N2_D1 = 64, N2_D2 = 96, N2_COLS = 176;
+constexpr int NSM_BAR = (NIMG_BYTES + 15) / 16 * 16, NSM_TMEM = NSM_BAR + 2 * 8, NSMEM_BYTES = NSM_TMEM + 16;
+
+__global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
+    const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ in_ptr, int64_t num_nodes, int64_t num_out,
+    int32_t chunks_out, int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
+    const uint8_t* __restrict__ wimg, const float* __restrict__ pinit, uint4* __restrict__ xl_next,
+    float* __restrict__ prow, float* __restrict__ x_out, int32_t step, int32_t* __restrict__ sched,
+    const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax, float scale_target, int32_t* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NSM_TMEM);
+  // scale inputs first: their latency overlaps the image copy
+  const float a_t = __uint_as_float(amax[step]), x_t = __uint_as_float(xmax[step]);
+  const float x_tm1 = step > 1 ? __uint_as_float(xmax[step - 1]) : 0.f;
+  for (int i = tid; i < NIMG_BYTES / 16; i += NT2_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  const int s_next = scale_for(a_t, x_t, x_tm1, scale_target);
+  const float sig_next = pow2i(-s_next);
+  if (blockIdx.x == 0 && tid == 0) sched[step + 1] = s_next;
+  // the flow vectors enter the node Linear in the scale of the step that produced the messages, 2^-FLOW_SHIFT lower
+  const int s_flow = sched[step] + FLOW_SHIFT;
+  const float sig_flow = pow2i(-s_flow), inv_sig_flow = pow2i(s_flow);
+
+  const int g = warp >> 2, wq = warp & 3;
+  const uint32_t tcol = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * N2_COLS;
+  const uint32_t tlane = tcol + ((uint32_t)(wq * 32) << 16);
+  uint64_t* d_ready = &bars[g];
+  uint32_t pd = 0;
+  const float* s_bn = reinterpret_cast<const float*>(smem + NOFF_F32);
+  const uint64_t dzero = smem_desc_kmajor(0, 128, 256);
+  const uint32_t img = smem_u32(smem);
+  const int64_t gmask = ((int64_t)1 << chunk_shift) - 1;
+  float mx = 0.f;
+  int ovf = 0;
+
+  auto issue = [&](int layer) {                                         // after the group's operands are in TMEM
+    tc_wait_st();
+    tc_fence_before();
+    named_barrier(1 + g, 128);
+    if (wq == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        auto bd = [&](int off) { return dzero + (uint64_t)((img + off) >> 4); };
+        if (layer == 1) {
+          constexpr uint32_t id = idesc_f16(128, DN);
+#pragma unroll
+          for (int ks = 0; ks < NW_KS; ++ks) {
+            mma_ts(tcol + N2_D1, tcol + N2_A1L + 8 * ks, bd(NOFF_NWH + ks * NW_SLAB), id, ks == 0 ? 0u : 1u);
+            mma_ts(tcol + N2_D1, tcol + N2_A1H + 8 * ks, bd(NOFF_NWL + ks * NW_SLAB), id, 1u);
+          }
+          mma_ts_sd(tcol + N2_D1, tcol + N2_A1H, bd(NOFF_NWH), id);
+#pragma unroll
+          for (int ks = 1; ks < NW_KS; ++ks) mma_ts(tcol + N2_D1, tcol + N2_A1H + 8 * ks, bd(NOFF_NWH + ks * NW_SLAB), id, 1u);
+        } else {
+          constexpr uint32_t id = idesc_f16(128, EH);
+#pragma unroll
+          for (int ks = 0; ks < PW_KS; ++ks) {
+            mma_ts(tcol + N2_D2, tcol + N2_D1 + 16 + 8 * ks, bd(NOFF_PWH + ks * PW_SLAB), id, ks == 0 ? 0u : 1u);
+            mma_ts(tcol + N2_D2, tcol + N2_D1 + 8 * ks, bd(NOFF_PWL + ks * PW_SLAB), id, 1u);
+          }
+          mma_ts_sd(tcol + N2_D2, tcol + N2_D1, bd(NOFF_PWH), id);
+          mma_ts(tcol + N2_D2, tcol + N2_D1 + 8, bd(NOFF_PWH + PW_SLAB), id, 1u);
+        }
+        mma_commit(d_ready);
+      }
+      __syncwarp();
+    }
+  };
+  // 32 floats of one row (128 B, per-thread contiguous)
+  auto load_row = [&](const float* p, float (&v)[DN]) {
+#pragma unroll
+    for (int q = 0; q < DN / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  };
+  // one direction's flow vector of node r -> split halves -> A operand columns [col_h, col_h + 16), [col_l, col_l + 16)
+  auto gather_flow = [&](int64_t r, int d, int64_t s0, int64_t s1, bool live, int col_h, int col_l) {
+    const int64_t seg_base = d == 0 ? num_out : 0;
+    const int64_t chunk_off = d == 0 ? chunks_out : 0;
+    float v[DN];
+#pragma unroll
+    for (int i = 0; i < DN; ++i) v[i] = 0.f;
+    if (live && s1 > s0) {
+      const int64_t rel0 = s0 - seg_base;
+      const int64_t ca = rel0 >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
+      if (ca == cb) {
+        load_row(flow + r * 2 * DN + d * DN, v);
+      } else {
+        const bool first_in_chunk = (rel0 & gmask) == 0;
+        load_row(part + ((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN, v);
+        for (int64_t t = ca + 1; t <= cb; ++t) {                        // granule order = slot order
+          float u[DN];
+          load_row(part + ((chunk_off + t) * 2) * DN, u);
+#pragma unroll
+          for (int i = 0; i < DN; ++i) v[i] += u[i];
+        }
+      }
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = v[2 * j] * sig_flow, b = v[2 * j + 1] * sig_flow;
+      split2s(a, b, hi[j], lo[j]);
+      if (!(fmaxf(a, b) < 65000.f)) ovf = 1;
+    }
+    const uint32_t h0[8] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]};
+    const uint32_t h1[8] = {hi[8], hi[9], hi[10], hi[11], hi[12], hi[13], hi[14], hi[15]};
+    const uint32_t l0[8] = {lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]};
+    const uint32_t l1[8] = {lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]};
+    tmem_st8(tlane + col_h, h0); tmem_st8(tlane + col_h + 8, h1);
+    tmem_st8(tlane + col_l, l0); tmem_st8(tlane + col_l + 8, l1);
+  };
+
+  const int64_t tiles = (num_nodes + TS - 1) / TS;
+  for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < tiles; t += (int64_t)gridDim.x * 2) {
+    const int64_t r = t * TS + wq * 32 + lane;
+    const bool live = r < num_nodes;
+    const int64_t rc = live ? r : num_nodes - 1;
+    const int32_t i0 = in_ptr[rc], i1 = in_ptr[rc + 1], o0 = out_ptr[rc], o1 = out_ptr[rc + 1];
+    // ---- flows -> A operand: K order [flow_in | flow_out] (models/mpn.py:97)
+    gather_flow(rc, 0, i0, i1, live, N2_A1H, N2_A1L);
+    gather_flow(rc, 1, o0, o1, live, N2_A1H + 16, N2_A1L + 16);
+    issue(1);
+    // ---- epilogue 1: x' = ReLU(D1 + bn); split rows in the next step's scale (global + A operand of the row term)
+    mbar_wait(d_ready, pd); pd ^= 1;
+    tc_fence_after();
+    {
+      uint32_t acc[32];
+      tmem_ld16(tlane + N2_D1, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+      tmem_ld16(tlane + N2_D1 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+      tc_wait_ld();
+      float xn[DN];
+#pragma unroll
+      for (int i = 0; i < DN; ++i) { xn[i] = fmaxf(fmaf(__uint_as_float(acc[i]), inv_sig_flow, s_bn[i]), 0.f); mx = live ? fmaxf(mx, xn[i]) : mx; }
+      if (live && x_out != nullptr) {
+#pragma unroll
+        for (int q = 0; q < DN / 4; ++q)
+          reinterpret_cast<float4*>(x_out + r * DN)[q] = make_float4(xn[4 * q], xn[4 * q + 1], xn[4 * q + 2], xn[4 * q + 3]);
+      }
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = xn[2 * j] * sig_next, b = xn[2 * j + 1] * sig_next;
+        split2s(a, b, hi[j], lo[j]);
+        if (!(fmaxf(a, b) < 65000.f)) ovf = live ? 1 : ovf;
+      }
+      const uint32_t h0[8] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]};
+      const uint32_t h1[8] = {hi[8], hi[9], hi[10], hi[11], hi[12], hi[13], hi[14], hi[15]};
+      const uint32_t l0[8] = {lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]};
+      const uint32_t l1[8] = {lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]};
+      tmem_st8(tlane + N2_D1, h0); tmem_st8(tlane + N2_D1 + 8, h1);                 // K = 32: hi 16 columns
+      tmem_st8(tlane + N2_D1 + 16, l0); tmem_st8(tlane + N2_D1 + 24, l1);           //         lo 16 columns
+      issue(2);
+      if (live) {                                                        // [hi(32 halfs) | lo(32 halfs)] = 128 B
+        uint4* dst = xl_next + r * 8;
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);     dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        dst[2] = make_uint4(hi[8], hi[9], hi[10], hi[11]);   dst[3] = make_uint4(hi[12], hi[13], hi[14], hi[15]);
+        dst[4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);     dst[5] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        dst[6] = make_uint4(lo[8], lo[9], lo[10], lo[11]);   dst[7] = make_uint4(lo[12], lo[13], lo[14], lo[15]);
+      }
+    }
+    // ---- epilogue 2: prow = (pinit + W0[:, 32:64] x') * sigma_next = fma(pinit, sigma, D2)  (D2 is in the scaled domain)
+    float pin[16];
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(pinit + r * EH + 4 * q);
+        pin[4 * q] = v.x; pin[4 * q + 1] = v.y; pin[4 * q + 2] = v.z; pin[4 * q + 3] = v.w;
+      }
+    }
+    mbar_wait(d_ready, pd); pd ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < EH / 16; ++ch) {
+      uint32_t acc[16];
+      tmem_ld16(tlane + N2_D2 + 16 * ch, acc);
+      float nxt[16];
+      if (live && ch + 1 < EH / 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(pinit + r * EH + 16 * (ch + 1) + 4 * q);
+          nxt[4 * q] = v.x; nxt[4 * q + 1] = v.y; nxt[4 * q + 2] = v.z; nxt[4 * q + 3] = v.w;
+        }
+      }
+      tc_wait_ld();
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(prow + r * EH + 16 * ch)[q] =
+              make_float4(fmaf(pin[4 * q], sig_next, __uint_as_float(acc[4 * q])), fmaf(pin[4 * q + 1], sig_next, __uint_as_float(acc[4 * q + 1])),
+                          fmaf(pin[4 * q + 2], sig_next, __uint_as_float(acc[4 * q + 2])), fmaf(pin[4 * q + 3], sig_next, __uint_as_float(acc[4 * q + 3])));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pin[i] = nxt[i];
+    }
+    tc_fence_before();
+    named_barrier(1 + g, 128);                                          // D2 / A columns are rewritten by the next tile
+  }
+  atomic_max_f32(xmax + step + 1, mx);
+  if (ovf) atomicOr(status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
 // e (fp32 [E,16], slot order) -> split rows [hi(16) | lo(16)] halfs
@@ -341,8 +635,9 @@ __global__ void split_edges_kernel(const float* __restrict__ e, int64_t num_edge
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 v = __ldg(p + q);
-      split2s(v.x, v.y, hi[2 * q], lo[2 * q]);
-      split2s(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+      const float sc = pow2i(-INIT_SHIFT);
+      split2s(v.x * sc, v.y * sc, hi[2 * q], lo[2 * q]);
+      split2s(v.z * sc, v.w * sc, hi[2 * q + 1], lo[2 * q + 1]);
       if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) < 65000.f)) ovf = 1;
     }
     out[s * 4 + 0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -463,41 +758,38 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM3_TMEM);
   // this step's scale (uniform): operands are true values x sigma
   const int s_cur = a.sched[a.step];
-  const int s_prev = a.step > 1 ? a.sched[a.step - 1] : 0;
+  const int s_prev = a.step > 1 ? a.sched[a.step - 1] : INIT_SHIFT;   // step 1 reads e_init rows as the latent state
   const float sigma = pow2i(-s_cur), inv_sigma = pow2i(s_cur);
   {
     const uint4* src = reinterpret_cast<const uint4*>(dir_out ? a.wimg_out : a.wimg_in);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    if (s_cur == 0) {
-      for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) dst[i] = __ldg(src + i);
-    } else {
-      // the slabs that multiply the constant (unscaled) x_init / e_init rows carry sigma themselves, and so do the
-      // biases; the classifier's output layer undoes it (all powers of two: exact up to fp16 subnormal rounding)
-      const __half2 sg = __float2half2_rn(sigma);
-      for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) {
-        uint4 v = __ldg(src + i);
-        const int o = i * 16;
-        if (o < OFF_F32) {
-          bool init_slab = false;
-          if (o < OFF_L2H) { const int ks = (o % (L1_KS * L1_SLAB)) / L1_SLAB; init_slab = ks <= 1 || ks == 4; }
-          else if (o >= OFF_L3H && o < OFF_L4H) { const int ks = ((o - OFF_L3H) % (L3_KS * L3_SLAB)) / L3_SLAB; init_slab = ks <= 1; }
-          if (init_slab) {
-            __half2* h = reinterpret_cast<__half2*>(&v);
+    // The slabs that multiply the constant x_init / e_init rows (stored x 2^-INIT_SHIFT) carry 2^(INIT_SHIFT - s) themselves,
+    // and the biases carry sigma; the classifier's output layer undoes it (all powers of two: exact).
+    const __half2 sg = __float2half2_rn(pow2i(INIT_SHIFT - s_cur));
+    for (int i = tid; i < IMG_BYTES / 16; i += NTHREADS3) {
+      uint4 v = __ldg(src + i);
+      const int o = i * 16;
+      if (o < OFF_F32) {
+        bool init_slab = false;
+        if (o < OFF_L2H) { const int ks = (o % (L1_KS * L1_SLAB)) / L1_SLAB; init_slab = ks <= 1 || ks == 4; }
+        else if (o >= OFF_L3H && o < OFF_L4H) { const int ks = ((o - OFF_L3H) % (L3_KS * L3_SLAB)) / L3_SLAB; init_slab = ks <= 1; }
+        if (init_slab) {
+          __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], sg);
-          }
-        } else {
-          float* f = reinterpret_cast<float*>(&v);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int fi = (o - OFF_F32) / 4 + q;
-            if (fi < F_CW0 || (fi >= F_CB0 && fi < F_CW1)) f[q] *= sigma;            // b1, fb0, fb1, cb0
-            else if (fi >= F_CW1 && fi < F_CB1) f[q] *= inv_sigma;                   // cw1
-          }
+          for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], sg);
         }
-        dst[i] = v;
+      } else if (s_cur != 0) {
+        float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int fi = (o - OFF_F32) / 4 + q;
+          if (fi < F_CW0 || (fi >= F_CB0 && fi < F_CW1)) f[q] *= sigma;            // b1, fb0, fb1, cb0
+          else if (fi >= F_CW1 && fi < F_CB1) f[q] *= inv_sigma;                   // cw1
+        }
       }
+      dst[i] = v;
     }
+    if (s_cur > INIT_SHIFT + 14 && tid == 0) atomicOr(a.status, 1);     // the slab factor would leave the normal fp16 range
   }
   if (tid == 0) {
     for (int i = 0; i < NG3; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[NG3 + i], 4); }
@@ -909,7 +1201,7 @@ struct TcWorkspace {
   float* pinit; float* prow;
   uint4* ei; uint4* es;
   float* flow; float* part;
-  uint8_t* wimg_out; uint8_t* wimg_in;
+  uint8_t* wimg_out; uint8_t* wimg_in; uint8_t* wimg_node;
   int32_t* sched; uint32_t* amax; uint32_t* xmax;      // range bookkeeping, MAX_STEPS + 8 entries each (contiguous)
 };
 
@@ -928,6 +1220,7 @@ static int64_t carve(void* ws, int64_t n, int64_t e, TcWorkspace* out) {
   w.part = cv.take<float>(chunks * 2 * DN);
   w.wimg_out = cv.take<uint8_t>(IMG_BYTES);
   w.wimg_in = cv.take<uint8_t>(IMG_BYTES);
+  w.wimg_node = cv.take<uint8_t>(NIMG_BYTES);
   w.sched = cv.take<int32_t>(3 * (MAX_STEPS + 8));
   w.amax = reinterpret_cast<uint32_t*>(w.sched) + (MAX_STEPS + 8);
   w.xmax = w.amax + (MAX_STEPS + 8);
@@ -979,9 +1272,12 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   MPN_CUDA(cudaFuncSetAttribute(tc::mp_edge_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM3_BYTES));
   MPN_CUDA(cudaMemsetAsync(m.sched, 0, 3 * (tc::MAX_STEPS + 8) * 4, s));
   const int sms = sm_count();
-  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, 1); count_launch();
+  tc::pack_weights_kernel<<<16, 256, 0, s>>>(*w, m.wimg_out, m.wimg_in, m.wimg_node, 1, status); count_launch();
   const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 4);
-  const unsigned ngrid_node = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sms * 2);   // node weights in registers: 2 CTAs/SM
+  const unsigned ngrid_node = (unsigned)std::min<int64_t>(ceil_div(n, 8 * tc::NODE_NB), (int64_t)sms * 2);
+  const unsigned ngrid_node2 = (unsigned)std::min<int64_t>(ceil_div(ceil_div(n, tc::TS), 2), (int64_t)sms);
+  static const bool node_simt = getenv("MPN_NODE_SIMT") != nullptr;      // development switch: FFMA2 node kernel
+  static const float scale_target = getenv("MPN_SCALE_TARGET") ? (float)atof(getenv("MPN_SCALE_TARGET")) : tc::SCALE_TARGET;
   tc::prep_nodes_kernel<<<ngrid, 256, 0, s>>>(x_init, n, w->edge_w0, w->edge_b0, m.xi, m.xl[0], m.pinit, m.prow, m.xmax, status);
   count_launch();
   if (e > 0) {
@@ -1031,10 +1327,17 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       if (profiling()) profile_mark(0, false, s);
     }
     if (profiling()) profile_mark(1, true, s);
-    tc::node_tc_kernel<<<ngrid_node, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
-                                             (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
-                                             w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
-                                             step == num_steps ? x_out : nullptr, step, m.sched, m.amax, m.xmax, status);
+    if (node_simt) {
+      tc::node_tc_kernel<<<ngrid_node, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
+                                               (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
+                                               w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
+                                               step == num_steps ? x_out : nullptr, step, m.sched, m.amax, m.xmax, scale_target, status);
+    } else {
+      tc::node_tc2_kernel<<<ngrid_node2, tc::NT2_THREADS, tc::NSMEM_BYTES, s>>>(
+          g->out_ptr, g->in_ptr, n, g->num_out, (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part,
+          m.wimg_node, m.pinit, reinterpret_cast<uint4*>(xl_next), m.prow, step == num_steps ? x_out : nullptr, step,
+          m.sched, m.amax, m.xmax, scale_target, status);
+    }
     count_launch();
     if (profiling()) profile_mark(1, false, s);
     MPN_LAUNCH_CHECK();

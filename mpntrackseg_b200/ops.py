@@ -336,7 +336,7 @@ def mp_forward(cw, layout, x_init, e_init, num_steps, first_class_step, want_sta
 
     engine: 'tc' = tcgen05 tensor-core kernels (fp16 hi/lo split operands in a per-step power-of-two
     scale, fp32 accumulate), 'fp32' = fp32 SIMT kernels, 'auto' (default) = 'tc', rerun on 'fp32' if an
-    activation still left the fp16 range (one-step growth beyond the 64x headroom of the scale).  status: optional int32[1] device tensor: the overflow flag is left there for the
+    activation still left the fp16 range (one-step growth beyond the 1024x headroom of the scale).  status: optional int32[1] device tensor: the overflow flag is left there for the
     caller (no host sync, no fallback here)."""
     engine = engine or default_engine()
     x_init = _req(x_init, torch.float32, 'x_init')

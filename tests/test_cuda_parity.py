@@ -459,8 +459,12 @@ def test_tc_engine_scales_activations_beyond_the_fp16_range():
         P[k + '.weight'] = P[k + '.weight'] * 32.0
         P[k + '.bias'] = P[k + '.bias'] * 32.0
     ref_g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds)
+    # At these magnitudes the fp32 oracle itself sits 6.5e-4 (relative) from the exact result, so two fp32-grade
+    # evaluations can differ by more than the 1e-3 bar; the oracle is evaluated in fp64 here (same formulas, same
+    # fp32 weights and inputs), which leaves the bar to the CUDA path alone (it lands at ~7e-4).
     with torch.no_grad():
-        ref = mpn_ref.mpn_forward(P, mp, win.x, ref_g['edge_index'], ref_g['edge_attr'], return_state=True)
+        ref = mpn_ref.mpn_forward({k: v.double() for k, v in P.items()}, mp, win.x.double(), ref_g['edge_index'],
+                                  ref_g['edge_attr'].double(), return_state=True)
     assert float(ref['node_state'].max()) > 10 * 65504.0, 'the case must exceed the fp16 range by 10x'
     g = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
     assert torch.equal(g.edge_index.cpu(), ref_g['edge_index'])
@@ -515,25 +519,26 @@ def test_bench_workload_stays_on_the_tensor_core_path():
 
 
 def test_tc_engine_reports_fp16_overflow_and_auto_falls_back():
-    """A one-step jump beyond the 64x headroom of the per-step scale (node Linear x 4000): engine='tc' raises,
-    'auto' reruns on the fp32 kernels."""
+    """A one-step jump beyond the 1024x headroom of the per-step scale (node Linear x 3e4), or a weight that has no
+    finite fp16 image (x 1e6): engine='tc' raises, 'auto' reruns on the fp32 kernels."""
     c = load_case('kitti_shape')
     win, gold = c['win'], c['gold']
     mp = dict(c['mp'], num_enc_steps=3, num_class_steps=2)
-    P = {k: (v * 4000.0 if k.startswith('MPNet.node_model.node_model.0') else v) for k, v in c['P'].items()}
     data = Data()
     data.x = win.x.to(dev())
     data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
     data.edge_attr = torch.from_numpy(gold['edge_attr']).to(dev())
-    with torch.no_grad():
-        ref = make_model(mp, P, 'fp32')(data)['classified_edges'][-1]
-        assert torch.isfinite(ref).all()
-        with pytest.raises(OverflowError):
-            make_model(mp, P, 'tc')(data)
-        with pytest.warns(UserWarning, match='fp16 range'):
-            auto = make_model(mp, P, 'auto')(data)['classified_edges'][-1]
-    # 'auto' keeps the tensor-core node encoder (no overflow there), so compare to tolerance, not bitwise
-    np.testing.assert_allclose(auto.cpu().numpy(), ref.cpu().numpy(), rtol=1e-3, atol=1e-3)
+    for factor in (3.0e4, 1.0e6):
+        P = {k: (v * factor if k.startswith('MPNet.node_model.node_model.0') else v) for k, v in c['P'].items()}
+        with torch.no_grad():
+            ref = make_model(mp, P, 'fp32')(data)['classified_edges'][-1]
+            assert torch.isfinite(ref).all()
+            with pytest.raises(OverflowError):
+                make_model(mp, P, 'tc')(data)
+            with pytest.warns(UserWarning, match='fp16 range'):
+                auto = make_model(mp, P, 'auto')(data)['classified_edges'][-1]
+        # 'auto' keeps the tensor-core node encoder (no overflow there), so compare to tolerance, not bitwise
+        np.testing.assert_allclose(auto.cpu().numpy(), ref.cpu().numpy(), rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
 
 
 def test_edge_and_node_model_forward_match_oracle():
