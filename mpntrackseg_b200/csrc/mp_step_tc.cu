@@ -495,28 +495,30 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
       v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
   };
-  // one direction's flow vector of node r -> split halves -> A operand columns [col_h, col_h + 16), [col_l, col_l + 16)
+  // one direction's flow vector of node r -> split halves -> A operand columns [col_h, col_h + 16), [col_l, col_l + 16).
+  // The first three pieces (row sum, or granule partials) are loaded together from always-valid addresses and masked,
+  // so that their latencies overlap; rows that span more than three granules (degree > 32) take the loop.
   auto gather_flow = [&](int64_t r, int d, int64_t s0, int64_t s1, bool live, int col_h, int col_l) {
     const int64_t seg_base = d == 0 ? num_out : 0;
     const int64_t chunk_off = d == 0 ? chunks_out : 0;
-    float v[DN];
+    const bool has = live && s1 > s0;
+    const int64_t rel0 = s0 - seg_base;
+    const int64_t ca = rel0 >> chunk_shift, cb = has ? (s1 - 1 - seg_base) >> chunk_shift : ca;
+    const int64_t more = cb - ca;
+    const bool first_in_chunk = (rel0 & gmask) == 0;
+    const float* p0 = more == 0 ? flow + r * 2 * DN + d * DN : part + ((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN;
+    const float* pp = part + ((chunk_off + ca + 1) * 2) * DN;
+    float v[DN], u1[DN], u2[DN];
+    load_row(has ? p0 : flow, v);
+    load_row(has && more >= 1 ? pp : flow, u1);
+    load_row(has && more >= 2 ? pp + 2 * DN : flow, u2);
+    const bool k1 = has && more >= 1, k2 = has && more >= 2;
 #pragma unroll
-    for (int i = 0; i < DN; ++i) v[i] = 0.f;
-    if (live && s1 > s0) {
-      const int64_t rel0 = s0 - seg_base;
-      const int64_t ca = rel0 >> chunk_shift, cb = (s1 - 1 - seg_base) >> chunk_shift;
-      if (ca == cb) {
-        load_row(flow + r * 2 * DN + d * DN, v);
-      } else {
-        const bool first_in_chunk = (rel0 & gmask) == 0;
-        load_row(part + ((chunk_off + ca) * 2 + (first_in_chunk ? 0 : 1)) * DN, v);
-        for (int64_t t = ca + 1; t <= cb; ++t) {                        // granule order = slot order
-          float u[DN];
-          load_row(part + ((chunk_off + t) * 2) * DN, u);
+    for (int i = 0; i < DN; ++i) v[i] = ((has ? v[i] : 0.f) + (k1 ? u1[i] : 0.f)) + (k2 ? u2[i] : 0.f);   // + 0 is exact: granule order kept
+    for (int64_t t = ca + 3; t <= cb; ++t) {
+      load_row(part + ((chunk_off + t) * 2) * DN, u1);
 #pragma unroll
-          for (int i = 0; i < DN; ++i) v[i] += u[i];
-        }
-      }
+      for (int i = 0; i < DN; ++i) v[i] += u1[i];
     }
     uint32_t hi[16], lo[16];
 #pragma unroll
@@ -543,6 +545,13 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
     gather_flow(rc, 0, i0, i1, live, N2_A1H, N2_A1L);
     gather_flow(rc, 1, o0, o1, live, N2_A1H + 16, N2_A1L + 16);
     issue(1);
+    // the hoisted-term inputs of this node: all 20 loads in flight while the node Linear runs
+    float pin[EH];
+#pragma unroll
+    for (int q = 0; q < EH / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(pinit + rc * EH + 4 * q);
+      pin[4 * q] = v.x; pin[4 * q + 1] = v.y; pin[4 * q + 2] = v.z; pin[4 * q + 3] = v.w;
+    }
     // ---- epilogue 1: x' = ReLU(D1 + bn); split rows in the next step's scale (global + A operand of the row term)
     mbar_wait(d_ready, pd); pd ^= 1;
     tc_fence_after();
@@ -582,38 +591,22 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
       }
     }
     // ---- epilogue 2: prow = (pinit + W0[:, 32:64] x') * sigma_next = fma(pinit, sigma, D2)  (D2 is in the scaled domain)
-    float pin[16];
-    if (live) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(pinit + r * EH + 4 * q);
-        pin[4 * q] = v.x; pin[4 * q + 1] = v.y; pin[4 * q + 2] = v.z; pin[4 * q + 3] = v.w;
-      }
-    }
     mbar_wait(d_ready, pd); pd ^= 1;
     tc_fence_after();
 #pragma unroll
     for (int ch = 0; ch < EH / 16; ++ch) {
       uint32_t acc[16];
       tmem_ld16(tlane + N2_D2 + 16 * ch, acc);
-      float nxt[16];
-      if (live && ch + 1 < EH / 16) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(pinit + r * EH + 16 * (ch + 1) + 4 * q);
-          nxt[4 * q] = v.x; nxt[4 * q + 1] = v.y; nxt[4 * q + 2] = v.z; nxt[4 * q + 3] = v.w;
-        }
-      }
       tc_wait_ld();
       if (live) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
+          const int c = 16 * ch + 4 * q;
           reinterpret_cast<float4*>(prow + r * EH + 16 * ch)[q] =
-              make_float4(fmaf(pin[4 * q], sig_next, __uint_as_float(acc[4 * q])), fmaf(pin[4 * q + 1], sig_next, __uint_as_float(acc[4 * q + 1])),
-                          fmaf(pin[4 * q + 2], sig_next, __uint_as_float(acc[4 * q + 2])), fmaf(pin[4 * q + 3], sig_next, __uint_as_float(acc[4 * q + 3])));
+              make_float4(fmaf(pin[c], sig_next, __uint_as_float(acc[4 * q])), fmaf(pin[c + 1], sig_next, __uint_as_float(acc[4 * q + 1])),
+                          fmaf(pin[c + 2], sig_next, __uint_as_float(acc[4 * q + 2])), fmaf(pin[c + 3], sig_next, __uint_as_float(acc[4 * q + 3])));
+        }
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pin[i] = nxt[i];
     }
     tc_fence_before();
     named_barrier(1 + g, 128);                                          // D2 / A columns are rewritten by the next tile
