@@ -727,7 +727,8 @@ constexpr int G3_XI = 0, G3_XL = 4 * A_SLAB, G3_MSG = 8 * A_SLAB, G3_BYTES = 12 
 constexpr int SM3_GRP = (IMG_BYTES + 1023) / 1024 * 1024;                      // swizzled tiles need 1 KB alignment
 constexpr int SM3_BAR = SM3_GRP + NG3 * G3_BYTES;                              // d_ready[3], xc_ready[3]
 constexpr int SM3_TMEM = SM3_BAR + 8 * 8;
-constexpr int SMEM3_BYTES = SM3_TMEM + 16;
+constexpr int SM3_ROWS = SM3_TMEM + 16;                                         // int32 [24 warps][32]: slot -> row of the warp's quarter
+constexpr int SMEM3_BYTES = SM3_ROWS + NG3 * 8 * 32 * 4;
 
 __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_xi,
                                                                     const __grid_constant__ CUtensorMap tm_xl) {
@@ -807,8 +808,11 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
   const uint32_t grp_addr = smem_u32(grp);
   // this warp's private message buffer: 32 rows x 16 features (its half of the columns), bank-conflict-free
   // both for the row-major writes (lane = row) and the feature-major reads of the row sums
+  // Layout: row R (64 B) sits at physical row P = R ^ (R >> 4) (odd / even rows swapped in the upper granule, so that the two
+  // half-warps of the row sums hit disjoint banks) with its four 16-byte chunks XOR-swizzled by (P >> 1) & 3 (conflict-free
+  // 16-byte row writes).
   float* s_msg = reinterpret_cast<float*>(grp + G3_MSG) + (wq * 2 + hb) * 32 * 16;
-  auto msg_at = [&](int row, int f) { return s_msg + ((row ^ ((row >> 4) & 1)) << 4) + ((f + (row >> 1)) & 15); };
+  int32_t* s_rows = reinterpret_cast<int32_t*>(smem + SM3_ROWS) + warp * 32;
   uint64_t* d_ready = &bars[g];
   uint64_t* xc_ready = &bars[NG3 + g];                                  // 4 gathering warps arrive + 32 KB of TMA bytes
   uint32_t px = 0;
@@ -903,7 +907,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+      split2s_relu_add(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]), add[2 * j], add[2 * j + 1], hi[j], lo[j]);
       vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
     }
     tmem_st8(tlane + col, hi);
@@ -994,13 +998,18 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     const unsigned ends = (__ballot_sync(0xffffffffu, seg_end_here) >> (16 * sub)) & 0xffffu;
     const int64_t chunk_id = chunk_off + ((t.base + wq * 32 - seg_base) >> CHUNK3_SHIFT) + sub;
     const int f = 16 * hb + fl;
+    // message (16 sub + q, fl): physical row 16 sub + (q ^ sub), chunk (fl >> 2) ^ ((q >> 1) & 3)
+    const float* mb = s_msg + 256 * sub + (fl & 3);
+    const int rs = 16 * sub;                                                     // (q ^ sub) * 16 = 16 q +- 16 sub
+    const int c4 = 4 * (fl >> 2);
+    const int32_t* rows = s_rows + 16 * sub;
     float sum = 0.f;
     bool first_seg = true;
 #pragma unroll
     for (int q = 0; q < CHUNK3; ++q) {
-      const int32_t rq = __shfl_sync(0xffffffffu, t.r, 16 * sub + q);
-      sum += *msg_at(16 * sub + q, fl);
+      sum += mb[16 * q + ((q & 1) ? -rs : rs) + (c4 ^ (4 * ((q >> 1) & 3)))];
       if ((ends >> q) & 1u) {
+        const int32_t rq = rows[q];
         const bool starts_before = first_seg && r_prev == rq;
         const bool continues = q == cw - 1 && r_next == rq;
         if (!starts_before && !continues) a.flow[(int64_t)rq * 2 * DN + dir_off + f] = sum * inv_sigma;
@@ -1076,7 +1085,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+        split2s_relu_add(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]), add[2 * j], add[2 * j + 1], hi[j], lo[j]);
         vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
       }
       tmem_st8(tlane + T3_A3, hi);
@@ -1120,7 +1129,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          split2s_relu(__uint_as_float(acc[2 * j]) + add[2 * j], __uint_as_float(acc[2 * j + 1]) + add[2 * j + 1], hi[j], lo[j]);
+          split2s_relu_add(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]), add[2 * j], add[2 * j + 1], hi[j], lo[j]);
           vmax = __hmax2(vmax, *reinterpret_cast<const __half2*>(&hi[j]));
         }
 #pragma unroll
@@ -1147,11 +1156,17 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
       float add[16];
       ld_f32x16(add, s_f + F_FB1 + 16 * hb);
       tc_wait_ld();
+      // slots past the end of the slot range need no masking: nothing after the last row end is ever stored
+      float m[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float m = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
-        *msg_at(lane, j) = valid ? m : 0.f;
-      }
+      for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(acc[j]) + add[j], 0.f);
+      const int prow_ = lane ^ (lane >> 4);
+      float* mrow = s_msg + 16 * prow_;
+      const int sw = (prow_ >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(mrow + 4 * (c ^ sw)) = make_float4(m[4 * c], m[4 * c + 1], m[4 * c + 2], m[4 * c + 3]);
+      s_rows[lane] = cur.r;
     }
     __syncwarp();
     row_sums(cur);

@@ -197,6 +197,29 @@ __device__ __forceinline__ void split2s_relu(float a, float b, uint32_t& hi, uin
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((b - hf.y) * LO_SCALE), "f"((a - hf.x) * LO_SCALE));
 }
+// The same on (a + ba, b + bb) with the packed fp32x2 pipe (FADD2 / FMUL2: one instruction per pair): 7 instructions per
+// pair instead of 10.  Every packed operation is the IEEE rn operation of its two lanes, so the result is bit-identical.
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long r, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(r));
+}
+__device__ __forceinline__ void split2s_relu_add(float a, float b, float ba, float bb, uint32_t& hi, uint32_t& lo) {
+  unsigned long long t, d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pack2(a, b)), "l"(pack2(ba, bb)));
+  float tx, ty;
+  unpack2(t, tx, ty);
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(ty), "f"(tx));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(t), "l"(pack2(hf.x, hf.y)));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(d), "l"(pack2(LO_SCALE, LO_SCALE)));
+  float dx, dy;
+  unpack2(d, dx, dy);
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(dy), "f"(dx));
+}
 // D = A.B + D * 2^-LO_SHIFT (kind::f16 accumulator input scale)
 __device__ __forceinline__ void mma_ts_sd(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
   asm volatile(
