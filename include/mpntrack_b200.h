@@ -196,6 +196,8 @@ typedef struct {
   const float* node_w;   const float* node_b;    /* [dn, 2*dn]                    */
   const float* cls_w0;   const float* cls_b0;    /* [cls_h, de]                   */
   const float* cls_w1;   const float* cls_b1;    /* [1, cls_h]                    */
+  int32_t node_agg;      /* models/mpn.py:263-273 node_agg_fn: 0 = 'sum' (scatter_add), 1 = 'mean' (scatter_mean: sum /
+                            max(count, 1)), 2 = 'max' (scatter_max; messages are post-ReLU, empty segments give 0) */
 } mpn_core_weights;
 
 typedef struct {

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmpntrack_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i64, c_i32, c_f32, c_vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 c_i64p = C.POINTER(C.c_int64)
@@ -21,7 +21,7 @@ class CoreWeights(C.Structure):
                [(n, c_vp) for n in (
                    'edge_w0', 'edge_b0', 'edge_w1', 'edge_b1', 'fin_w0', 'fin_b0', 'fin_w1', 'fin_b1',
                    'fout_w0', 'fout_b0', 'fout_w1', 'fout_b1', 'node_w', 'node_b',
-                   'cls_w0', 'cls_b0', 'cls_w1', 'cls_b1')]
+                   'cls_w0', 'cls_b0', 'cls_w1', 'cls_b1')] + [('node_agg', c_i32)]
 
 
 class EdgeLayout(C.Structure):

@@ -69,14 +69,23 @@ def default_dataset_params(top_k_nns=50, frames_per_graph=15, reciprocal_k_nns=T
     }
 
 
-def _mlp_shapes(prefix, in_dim, dims, out):
-    """Linear layers sit at even Sequential slots when BN/Dropout are off
-    (reference: models/mlp.py:12-23)."""
+def _mlp_shapes(prefix, in_dim, dims, out, use_batchnorm=False, dropout_p=0):
+    """Sequential slots of ``MLP``: Linear [, BatchNorm1d], ReLU [, Dropout] per hidden layer; a layer of width 1 is
+    a bare Linear (reference: models/mlp.py:12-23)."""
     slot = 0
     for d in dims:
         out[f'{prefix}.fc_layers.{slot}.weight'] = (d, in_dim)
         out[f'{prefix}.fc_layers.{slot}.bias'] = (d,)
-        slot += 2 if d != 1 else 1
+        slot += 1
+        if d != 1:
+            if use_batchnorm:
+                for name, shape in (('weight', (d,)), ('bias', (d,)), ('running_mean', (d,)), ('running_var', (d,)),
+                                    ('num_batches_tracked', ())):
+                    out[f'{prefix}.fc_layers.{slot}.{name}'] = shape
+                slot += 1
+            slot += 1                                       # ReLU
+            if dropout_p != 0:
+                slot += 1
         in_dim = d
 
 
@@ -116,12 +125,13 @@ def param_shapes(model_params, core_only=False):
     cls = p['classifier_feats_dict']
     d = core_dims(p)
     out = OrderedDict()
+    bn = lambda dct: dict(use_batchnorm=dct.get('use_batchnorm', False), dropout_p=dct.get('dropout_p', 0))
     _mlp_shapes('encoder.node_model', enc['node_in_dim'],
-                list(enc['node_dims']) + [enc['node_out_dim']], out)
+                list(enc['node_dims']) + [enc['node_out_dim']], out, **bn(enc))
     _mlp_shapes('encoder.edge_model', enc['edge_in_dim'],
-                list(enc['edge_dims']) + [enc['edge_out_dim']], out)
+                list(enc['edge_dims']) + [enc['edge_out_dim']], out, **bn(enc))
     _mlp_shapes('classifier.edge_model', cls['edge_in_dim'],
-                list(cls['edge_dims']) + [cls['edge_out_dim']], out)
+                list(cls['edge_dims']) + [cls['edge_out_dim']], out, **bn(cls))
     if not core_only:
         ne = p['node_ext_encoder_feats_dict']
         _cnn_shapes('node_ext_encoder', ne['input_dim'], ne['dims'], ne['kernel_sizes'], out)
@@ -136,9 +146,9 @@ def param_shapes(model_params, core_only=False):
                     mh['kernel_sizes'], out)
         _cnn_shapes('mask_predictor.mask_predictor', mp['input_dim'], mp['dims'],
                     mp['kernel_sizes'], out, transposed=mp['transposed'])
-    _mlp_shapes('MPNet.edge_model.edge_model', d['edge_mlp_in'], d['edge_mlp_dims'], out)
-    _mlp_shapes('MPNet.node_model.flow_in_model', d['flow_mlp_in'], d['flow_mlp_dims'], out)
-    _mlp_shapes('MPNet.node_model.flow_out_model', d['flow_mlp_in'], d['flow_mlp_dims'], out)
+    _mlp_shapes('MPNet.edge_model.edge_model', d['edge_mlp_in'], d['edge_mlp_dims'], out, **bn(p['edge_model_feats_dict']))
+    _mlp_shapes('MPNet.node_model.flow_in_model', d['flow_mlp_in'], d['flow_mlp_dims'], out, **bn(p['node_model_feats_dict']))
+    _mlp_shapes('MPNet.node_model.flow_out_model', d['flow_mlp_in'], d['flow_mlp_dims'], out, **bn(p['node_model_feats_dict']))
     out['MPNet.node_model.node_model.0.weight'] = (d['dn'], 2 * d['dn'])
     out['MPNet.node_model.node_model.0.bias'] = (d['dn'],)
     if not core_only:

@@ -57,6 +57,7 @@ struct StepArgs {
   float* logits;                                // row of the logits output for this step or NULL
   int do_edge;                                  // 0: e' := e_cur (node update only)
   int do_node;                                  // 0: skip flow messages / aggregation
+  int agg;                                      // 0 sum, 1 mean (sums here, divided in the node kernel), 2 max
 };
 
 template <int N4>
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(TS) mp_edge_kernel(StepArgs a, mpn_core_weight
           }
           cur = rq; sum = 0.f; seg_first_t = q;
         }
-        if (q < cnt) sum += s_msg[q * W::MSG_LD + f];
+        if (q < cnt) sum = a.agg == 2 ? fmaxf(sum, s_msg[q * W::MSG_LD + f]) : sum + s_msg[q * W::MSG_LD + f];
       }
     }
     __syncthreads();
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) mp_node_kernel(const int32_t* __restrict_
                                                       const float* __restrict__ part,
                                                       const float* __restrict__ node_w,
                                                       const float* __restrict__ node_b,
-                                                      float* __restrict__ x_next) {
+                                                      float* __restrict__ x_next, int agg) {
   constexpr int DN = W::DN;
   __shared__ float s_w[2 * DN * DN];   // Wt[in][out]
   __shared__ float s_b[DN];
@@ -240,8 +241,12 @@ __global__ void __launch_bounds__(256) mp_node_kernel(const int32_t* __restrict_
         } else {
           const bool first_in_tile = (s0 - seg_base) % TS == 0;
           v = part[((tile_off + ta) * 2 + (first_in_tile ? 0 : 1)) * DN + lane];
-          for (int64_t t = ta + 1; t <= tb; ++t) v += part[((tile_off + t) * 2) * DN + lane];
+          for (int64_t t = ta + 1; t <= tb; ++t) {
+            const float u = part[((tile_off + t) * 2) * DN + lane];
+            v = agg == 2 ? fmaxf(v, u) : v + u;
+          }
         }
+        if (agg == 1) v = v / (float)(s1 - s0);            // scatter_mean: sum / count (count >= 1 here)
       }
       fl[d] = v;
     }
@@ -325,6 +330,7 @@ namespace mpn {
 
 static int check_core(const mpn_core_weights* w, const mpn_edge_layout* g, const char* who) {
   MPN_CHECK_ARG(w && g, "%s: null descriptor", who);
+  MPN_CHECK_ARG(w->node_agg >= 0 && w->node_agg <= 2, "%s: node_agg must be 0 (sum), 1 (mean) or 2 (max)", who);
   MPN_CHECK_ARG(is_shipped(w), "%s: fused kernels are built for widths dn=32 de=16 edge_h=80 "
                 "flow_h=56 cls_h=8 (got %d %d %d %d %d)", who, w->dn, w->de, w->edge_h, w->flow_h, w->cls_h);
   return MPN_OK;
@@ -354,7 +360,7 @@ static int launch_step(const mpn_core_weights* w, const mpn_edge_layout* g, cons
     a.slot_row = g->slot_row; a.slot_col = g->slot_col; a.slot_edge = g->slot_edge;
     a.num_edges = e; a.num_out = g->num_out; a.tiles_out = tiles_out; a.tiles_in = tiles_in;
     a.x_init = x_init; a.x_lat = x_cur; a.e_init = e_init; a.e_cur = e_cur; a.e_next = e_next;
-    a.flow = m.flow; a.part = m.part; a.logits = logits_row; a.do_edge = do_edge; a.do_node = do_node;
+    a.flow = m.flow; a.part = m.part; a.logits = logits_row; a.do_edge = do_edge; a.do_node = do_node; a.agg = w->node_agg;
     if (profiling()) profile_mark(0, true, s);
     mp_edge_kernel<W><<<grid, TS, W::SMEM_BYTES, s>>>(a, *w); count_launch();
     if (profiling()) profile_mark(0, false, s);
@@ -363,7 +369,7 @@ static int launch_step(const mpn_core_weights* w, const mpn_edge_layout* g, cons
     const unsigned ngrid = (unsigned)std::min<int64_t>(ceil_div(n * 32, 256), (int64_t)sm_count() * 8);
     if (profiling()) profile_mark(1, true, s);
     mp_node_kernel<W><<<ngrid, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out, tiles_out, m.flow,
-                                            m.part, w->node_w, w->node_b, x_next); count_launch();
+                                            m.part, w->node_w, w->node_b, x_next, w->node_agg); count_launch();
     if (profiling()) profile_mark(1, false, s);
   }
   MPN_LAUNCH_CHECK();

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256, 3) node_tc_kernel(const int32_t* __restri
                                                          __half* __restrict__ xl_next, float* __restrict__ prow,
                                                          float* __restrict__ x_out, int32_t step, int32_t* __restrict__ sched,
                                                          const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax,
-                                                         float scale_target, int32_t* __restrict__ status) {
+                                                         float scale_target, int32_t agg, int32_t* __restrict__ status) {
   __shared__ float s_w0[DN * EH];                                   // [i][o] over W0 columns 32..63
   __shared__ float s_wn[2 * DN * DN];                               // node Linear, [in][out]
   __shared__ __align__(16) float s_in[8][2 * DN][NODE_NB];          // per warp: [input feature][node]
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256, 3) node_tc_kernel(const int32_t* __restri
   // its granule partials added in granule order.  Branch-free: every piece is an unconditional load from a valid
   // address (masked to 0 when absent), so the loads of all nodes of the group are in flight together; only rows that
   // span more than four granules (degree > 48) take the loop.
-  struct FlowReq { float v0, v1, v2, v3; int64_t ca, cb; };
+  struct FlowReq { float v0, v1, v2, v3, inv_cnt; int64_t ca, cb; };
   const int64_t gmask = ((int64_t)1 << chunk_shift) - 1;
   auto issue_flow = [&](int64_t r, int d, int64_t s0, int64_t s1, bool live) {
     const int64_t seg_base = d == 0 ? num_out : 0;
@@ -302,14 +302,14 @@ __global__ void __launch_bounds__(256, 3) node_tc_kernel(const int32_t* __restri
     q.v2 = has && more >= 2 ? q.v2 : 0.f;
     q.v3 = has && more >= 3 ? q.v3 : 0.f;
     q.ca = chunk_off + ca; q.cb = chunk_off + cb;
+    q.inv_cnt = has ? 1.f / (float)(s1 - s0) : 1.f;                    // scatter_mean: / max(count, 1)
     return q;
   };
   auto finish_flow = [&](const FlowReq& q) {
-    float v = q.v0 + q.v1;                                              // + 0.f is exact: same sums as the piecewise form
-    v += q.v2;
-    v += q.v3;
-    for (int64_t t = q.ca + 4; t <= q.cb; ++t) v += part[(t * 2) * DN + lane];
-    return v;
+    // + 0.f / max(., 0.f) are exact on the non-negative messages: same results as the piecewise form
+    float v = agg == 2 ? fmaxf(fmaxf(q.v0, q.v1), fmaxf(q.v2, q.v3)) : ((q.v0 + q.v1) + q.v2) + q.v3;
+    for (int64_t t = q.ca + 4; t <= q.cb; ++t) { const float u = part[(t * 2) * DN + lane]; v = agg == 2 ? fmaxf(v, u) : v + u; }
+    return agg == 1 ? v * q.inv_cnt : v;
   };
   auto load_ptrs = [&](int64_t r0, int cnt) {
     // row pointers of the group's nodes (+1): lanes 0..NB hold in_ptr, lanes 16..16+NB out_ptr
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
     int32_t chunks_out, int chunk_shift, const float* __restrict__ flow, const float* __restrict__ part,
     const uint8_t* __restrict__ wimg, const float* __restrict__ pinit, uint4* __restrict__ xl_next,
     float* __restrict__ prow, float* __restrict__ x_out, int32_t step, int32_t* __restrict__ sched,
-    const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax, float scale_target, int32_t* __restrict__ status) {
+    const uint32_t* __restrict__ amax, uint32_t* __restrict__ xmax, float scale_target, int32_t agg, int32_t* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -513,12 +513,22 @@ __global__ void __launch_bounds__(NT2_THREADS, 1) node_tc2_kernel(
     load_row(has && more >= 1 ? pp : flow, u1);
     load_row(has && more >= 2 ? pp + 2 * DN : flow, u2);
     const bool k1 = has && more >= 1, k2 = has && more >= 2;
+    if (agg == 2) {
 #pragma unroll
-    for (int i = 0; i < DN; ++i) v[i] = ((has ? v[i] : 0.f) + (k1 ? u1[i] : 0.f)) + (k2 ? u2[i] : 0.f);   // + 0 is exact: granule order kept
+      for (int i = 0; i < DN; ++i) v[i] = fmaxf(fmaxf(has ? v[i] : 0.f, k1 ? u1[i] : 0.f), k2 ? u2[i] : 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DN; ++i) v[i] = ((has ? v[i] : 0.f) + (k1 ? u1[i] : 0.f)) + (k2 ? u2[i] : 0.f);   // + 0 is exact: granule order kept
+    }
     for (int64_t t = ca + 3; t <= cb; ++t) {
       load_row(part + ((chunk_off + t) * 2) * DN, u1);
 #pragma unroll
-      for (int i = 0; i < DN; ++i) v[i] += u1[i];
+      for (int i = 0; i < DN; ++i) v[i] = agg == 2 ? fmaxf(v[i], u1[i]) : v[i] + u1[i];
+    }
+    if (agg == 1 && has) {                                              // scatter_mean: sum / count
+      const float inv = 1.f / (float)(s1 - s0);
+#pragma unroll
+      for (int i = 0; i < DN; ++i) v[i] *= inv;
     }
     uint32_t hi[16], lo[16];
 #pragma unroll
@@ -677,6 +687,7 @@ struct TcArgs {
   int32_t step;              // 1-based step index
   const int32_t* sched;      // sched[t] = s_t, see "range bookkeeping"
   uint32_t* amax;            // amax[step] receives the largest true activation of this launch
+  int32_t agg;               // 0 sum, 1 mean (summed here, divided by the node kernel), 2 max
 };
 
 __device__ __forceinline__ void ld_f32x16(float (&d)[16], const float* __restrict__ p) {
@@ -1003,11 +1014,13 @@ __global__ void __launch_bounds__(NTHREADS3, 1) mp_edge_tc3_kernel(TcArgs a, con
     const int rs = 16 * sub;                                                     // (q ^ sub) * 16 = 16 q +- 16 sub
     const int c4 = 4 * (fl >> 2);
     const int32_t* rows = s_rows + 16 * sub;
+    const bool agg_max = a.agg == 2;
     float sum = 0.f;
     bool first_seg = true;
 #pragma unroll
     for (int q = 0; q < CHUNK3; ++q) {
-      sum += mb[16 * q + ((q & 1) ? -rs : rs) + (c4 ^ (4 * ((q >> 1) & 3)))];
+      const float mq = mb[16 * q + ((q & 1) ? -rs : rs) + (c4 ^ (4 * ((q >> 1) & 3)))];
+      sum = agg_max ? fmaxf(sum, mq) : sum + mq;
       if ((ends >> q) & 1u) {
         const int32_t rq = rows[q];
         const bool starts_before = first_seg && r_prev == rq;
@@ -1267,6 +1280,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
   MPN_CHECK_ARG(w->dn == 32 && w->de == 16 && w->edge_h == 80 && w->flow_h == 56 && w->cls_h == 8,
                 "mp_forward_tc: built for widths dn=32 de=16 edge_h=80 flow_h=56 cls_h=8 (got %d %d %d %d %d)", w->dn,
                 w->de, w->edge_h, w->flow_h, w->cls_h);
+  MPN_CHECK_ARG(w->node_agg >= 0 && w->node_agg <= 2, "mp_forward_tc: node_agg must be 0 (sum), 1 (mean) or 2 (max)");
   MPN_CHECK_ARG(num_steps >= 1 && num_steps <= tc::MAX_STEPS, "mp_forward_tc: num_steps must be in 1..%d (use mpn_mp_forward for 0)",
                 tc::MAX_STEPS);
   MPN_CHECK_ARG(ws && status, "mp_forward_tc: null workspace / status");
@@ -1328,7 +1342,7 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       a.logits = (logits && step >= first_class_step) ? logits + (int64_t)(step - first_class_step) * e : nullptr;
       a.wimg_out = m.wimg_out; a.wimg_in = m.wimg_in;
       a.status = status;
-      a.step = step; a.sched = m.sched; a.amax = m.amax;
+      a.step = step; a.sched = m.sched; a.amax = m.amax; a.agg = w->node_agg;
       if (profiling()) profile_mark(0, true, s);
       tc::mp_edge_tc3_kernel<<<grid3, tc::NTHREADS3, tc::SMEM3_BYTES, s>>>(a, tm_xi, tm_xl[(step - 1) & 1]);
       count_launch();
@@ -1339,12 +1353,12 @@ int mpn_mp_forward_tc(const mpn_core_weights* w, const mpn_edge_layout* g, const
       tc::node_tc_kernel<<<ngrid_node, 256, 0, s>>>(g->out_ptr, g->in_ptr, n, g->num_out,
                                                (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part, w->node_w,
                                                w->node_b, w->edge_w0, m.pinit, xl_next, m.prow,
-                                               step == num_steps ? x_out : nullptr, step, m.sched, m.amax, m.xmax, scale_target, status);
+                                               step == num_steps ? x_out : nullptr, step, m.sched, m.amax, m.xmax, scale_target, w->node_agg, status);
     } else {
       tc::node_tc2_kernel<<<ngrid_node2, tc::NT2_THREADS, tc::NSMEM_BYTES, s>>>(
           g->out_ptr, g->in_ptr, n, g->num_out, (int32_t)ceil_div(g->num_out, chunk), chunk_shift, m.flow, m.part,
           m.wimg_node, m.pinit, reinterpret_cast<uint4*>(xl_next), m.prow, step == num_steps ? x_out : nullptr, step,
-          m.sched, m.amax, m.xmax, scale_target, status);
+          m.sched, m.amax, m.xmax, scale_target, w->node_agg, status);
     }
     count_launch();
     if (profiling()) profile_mark(1, false, s);

@@ -18,15 +18,15 @@ from .mlp import MLP
 
 
 def _core_weight_tensors(edge_mlp, flow_in, flow_out, node_lin, cls_mlp):
-    e0, e1 = edge_mlp.linears()
-    i0, i1 = flow_in.linears()
-    o0, o1 = flow_out.linears()
-    c0, c1 = cls_mlp.linears()
-    return {'edge_w0': e0.weight, 'edge_b0': e0.bias, 'edge_w1': e1.weight, 'edge_b1': e1.bias,
-            'fin_w0': i0.weight, 'fin_b0': i0.bias, 'fin_w1': i1.weight, 'fin_b1': i1.bias,
-            'fout_w0': o0.weight, 'fout_b0': o0.bias, 'fout_w1': o1.weight, 'fout_b1': o1.bias,
+    (e0w, e0b), (e1w, e1b) = edge_mlp.effective_linears()
+    (i0w, i0b), (i1w, i1b) = flow_in.effective_linears()
+    (o0w, o0b), (o1w, o1b) = flow_out.effective_linears()
+    (c0w, c0b), (c1w, c1b) = cls_mlp.effective_linears()
+    return {'edge_w0': e0w, 'edge_b0': e0b, 'edge_w1': e1w, 'edge_b1': e1b,
+            'fin_w0': i0w, 'fin_b0': i0b, 'fin_w1': i1w, 'fin_b1': i1b,
+            'fout_w0': o0w, 'fout_b0': o0b, 'fout_w1': o1w, 'fout_b1': o1b,
             'node_w': node_lin.weight, 'node_b': node_lin.bias,
-            'cls_w0': c0.weight, 'cls_b0': c0.bias, 'cls_w1': c1.weight, 'cls_b1': c1.bias}
+            'cls_w0': c0w, 'cls_b0': c0b, 'cls_w1': c1w, 'cls_b1': c1b}
 
 
 class _NullClassifier(nn.Module):
@@ -40,6 +40,9 @@ class _NullClassifier(nn.Module):
     def linears(self):
         return [self.l0, self.l1]
 
+    def effective_linears(self):
+        return [(self.l0.weight, self.l0.bias), (self.l1.weight, self.l1.bias)]
+
 
 def _zeros_like_core(dn, de, edge_h, flow_h, device):
     """Placeholder tensors for the parts of ``mpn_core_weights`` a single sub-model does not own (the C
@@ -50,6 +53,16 @@ def _zeros_like_core(dn, de, edge_h, flow_h, device):
             'fout_w0': z(flow_h, 2 * dn + de), 'fout_b0': z(flow_h), 'fout_w1': z(dn, flow_h), 'fout_b1': z(dn),
             'node_w': z(dn, 2 * dn), 'node_b': z(dn),
             'cls_w0': z(8, de), 'cls_b0': z(8), 'cls_w1': z(1, 8), 'cls_b1': z(1)}
+
+
+def _agg_name(node_agg_fn):
+    """'sum' | 'mean' | 'max' from the model's ``node_agg_fn`` (the reference stores a lambda around the torch_scatter
+    function; here the config string is kept and the kernels switch on it).  reference: models/mpn.py:263-273"""
+    if node_agg_fn is None:
+        return 'sum'
+    if isinstance(node_agg_fn, str):
+        return node_agg_fn.lower()
+    raise NotImplementedError('node_agg_fn must be one of the strings the reference accepts (sum / mean / max)')
 
 
 def _split_reattached(x, edge_attr, dn, de):
@@ -69,11 +82,11 @@ class EdgeModel(nn.Module):
         self.edge_model = edge_model
 
     def forward(self, node_feats, edge_index, edge_attr):
-        e0, e1 = self.edge_model.linears()
-        de, edge_h = e1.out_features, e0.out_features
-        dn = (e0.in_features - 2 * de) // 4
-        named = _zeros_like_core(dn, de, edge_h, 56, e0.weight.device)
-        named.update(edge_w0=e0.weight, edge_b0=e0.bias, edge_w1=e1.weight, edge_b1=e1.bias)
+        (e0w, e0b), (e1w, e1b) = self.edge_model.effective_linears()
+        de, edge_h = e1w.shape[0], e0w.shape[0]
+        dn = (e0w.shape[1] - 2 * de) // 4
+        named = _zeros_like_core(dn, de, edge_h, 56, e0w.device)
+        named.update(edge_w0=e0w, edge_b0=e0b, edge_w1=e1w, edge_b1=e1b)
         cw, keep = ops.core_weights(named)
         xi, xl = _split_reattached(node_feats, edge_attr, dn, de)
         if edge_attr.shape[1] != 2 * de:
@@ -104,19 +117,16 @@ class TimeAwareNodeModel(nn.Module):
         self.node_agg_fn = node_agg_fn
 
     def forward(self, x, edge_index, edge_attr):
-        i0, i1 = self.flow_in_model.linears()
+        (i0w, i0b), (i1w, i1b) = self.flow_in_model.effective_linears()
         de = edge_attr.shape[1]
-        dn, flow_h = i1.out_features, i0.out_features
-        if i0.in_features != 2 * dn + de:
-            raise NotImplementedError(f'TimeAwareNodeModel expects x [N,{2 * dn}] and edge_attr [E,{i0.in_features - 2 * dn}]')
-        if self.node_agg_fn not in ('sum', None) and not callable(self.node_agg_fn):
-            raise NotImplementedError("node_agg_fn other than 'sum' goes through MOTMPNet (aggregation mode of the core)")
-        o0, o1 = self.flow_out_model.linears()
-        named = _zeros_like_core(dn, de, 80, flow_h, i0.weight.device)
-        named.update(fin_w0=i0.weight, fin_b0=i0.bias, fin_w1=i1.weight, fin_b1=i1.bias,
-                     fout_w0=o0.weight, fout_b0=o0.bias, fout_w1=o1.weight, fout_b1=o1.bias,
+        dn, flow_h = i1w.shape[0], i0w.shape[0]
+        if i0w.shape[1] != 2 * dn + de:
+            raise NotImplementedError(f'TimeAwareNodeModel expects x [N,{2 * dn}] and edge_attr [E,{i0w.shape[1] - 2 * dn}]')
+        (o0w, o0b), (o1w, o1b) = self.flow_out_model.effective_linears()
+        named = _zeros_like_core(dn, de, 80, flow_h, i0w.device)
+        named.update(fin_w0=i0w, fin_b0=i0b, fin_w1=i1w, fin_b1=i1b, fout_w0=o0w, fout_b0=o0b, fout_w1=o1w, fout_b1=o1b,
                      node_w=self.node_model[0].weight, node_b=self.node_model[0].bias)
-        cw, keep = ops.core_weights(named)
+        cw, keep = ops.core_weights(named, node_agg=_agg_name(self.node_agg_fn))
         if x.shape[1] != 2 * dn:
             raise NotImplementedError(f'TimeAwareNodeModel expects x [N,{2 * dn}] (reattach_initial_nodes = True)')
         layout = ops.edge_layout(edge_index, x.shape[0])
@@ -146,10 +156,11 @@ class MetaLayer(nn.Module):
             if self._null_cls is None:
                 dev = em.edge_model.linears()[0].weight.device
                 self._null_cls = [_NullClassifier(em.edge_model.linears()[-1].out_features, dev)]
+                self._null_cls[0].eval()
             classifier = self._null_cls[0]
         named = _core_weight_tensors(em.edge_model, nm.flow_in_model, nm.flow_out_model,
                                      nm.node_model[0], classifier)
-        return ops.core_weights(named)
+        return ops.core_weights(named, node_agg=_agg_name(nm.node_agg_fn))
 
     def forward(self, x, edge_index, edge_attr):
         cw, keep = self._weights()
@@ -292,8 +303,6 @@ class MOTMPNet(nn.Module):
         """reference: models/mpn.py:250-317"""
         agg = model_params['node_agg_fn']
         assert agg.lower() in ('mean', 'max', 'sum'), "node_agg_fn can only be 'max', 'mean' or 'sum'."
-        if agg != 'sum':
-            raise NotImplementedError("node_agg_fn other than 'sum' is not built into the fused kernel")
         self.reattach_initial_nodes = model_params['reattach_initial_nodes']
         self.reattach_initial_edges = model_params['reattach_initial_edges']
         if not (self.reattach_initial_nodes and self.reattach_initial_edges):
@@ -330,8 +339,8 @@ class MOTMPNet(nn.Module):
 
     def encode_pooled(self, pooled, engine=None, status=None):
         """Node MLP on already pooled features [N, C] (one launch for any number of windows)."""
-        lins = self.encoder.node_model.linears()
-        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins],
+        lins = self.encoder.node_model.effective_linears()
+        return ops.node_encoder(pooled, [w for w, _ in lins], [b for _, b in lins],
                                 engine=engine or self.engine, status=status)
 
     def encode_nodes_list(self, xs, engine=None, status=None):
@@ -347,12 +356,12 @@ class MOTMPNet(nn.Module):
             for x in xs:
                 ops.avgpool(x if x.dim() > 2 else x[:, :, None, None], out=pooled[off:off + x.shape[0]])
                 off += x.shape[0]
-        lins = self.encoder.node_model.linears()
-        return ops.node_encoder(pooled, [l.weight for l in lins], [l.bias for l in lins], engine=engine, status=status)
+        lins = self.encoder.node_model.effective_linears()
+        return ops.node_encoder(pooled, [w for w, _ in lins], [b for _, b in lins], engine=engine, status=status)
 
     def encode_edges(self, edge_attr, layout):
-        lins = self.encoder.edge_model.linears()
-        return ops.edge_encoder(edge_attr, layout, [l.weight for l in lins], [l.bias for l in lins])
+        lins = self.encoder.edge_model.effective_linears()
+        return ops.edge_encoder(edge_attr, layout, [w for w, _ in lins], [b for _, b in lins])
 
     def forward_batch(self, graphs, encoded=False):
         """Extension (not in the reference): evaluate several independent window graphs as one

@@ -295,9 +295,14 @@ def edge_encoder(edge_attr, layout, weights, biases):
 
 
 # ------------------------------------------------------------------ message passing
-def core_weights(named):
+NODE_AGG = {'sum': 0, 'mean': 1, 'max': 2}
+
+
+def core_weights(named, node_agg='sum'):
     """Build the mpn_core_weights struct from a dict of CUDA fp32 tensors keyed by the struct's
-    field names; returns (struct, keepalive list)."""
+    field names; returns (struct, keepalive list).  node_agg: 'sum' | 'mean' | 'max' (models/mpn.py:263-273)."""
+    if node_agg not in NODE_AGG:
+        raise ValueError(f"node_agg_fn can only be 'max', 'mean' or 'sum', got {node_agg!r}")
     keep = {k: _req(v, torch.float32, k) for k, v in named.items()}
     dn = keep['node_w'].shape[0]
     de = keep['edge_w1'].shape[0]
@@ -311,8 +316,9 @@ def core_weights(named):
     for k, shp in expect.items():
         if tuple(keep[k].shape) != shp:
             raise ValueError(f'{k}: expected shape {shp}, got {tuple(keep[k].shape)}')
-    for name, _ in CoreWeights._fields_[5:]:
+    for name, _ in CoreWeights._fields_[5:-1]:
         setattr(cw, name, keep[name].data_ptr())
+    cw.node_agg = NODE_AGG[node_agg]
     return cw, list(keep.values())
 
 

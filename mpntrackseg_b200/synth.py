@@ -104,6 +104,15 @@ def make_params(model_params, seed=0, gain=1.0, core_only=False, dtype=torch.flo
     out = OrderedDict()
     shapes = param_shapes(model_params, core_only=core_only)
     for name, shape in shapes.items():
+        if name.endswith('num_batches_tracked'):
+            out[name] = torch.tensor(100, dtype=torch.int64)
+            continue
+        if name.endswith('running_var') or (name.endswith('weight') and len(shape) == 1 and 'layer_norm' not in name):
+            out[name] = (0.5 + torch.rand(shape, generator=g, dtype=torch.float64)).to(dtype)      # BatchNorm scale / variance
+            continue
+        if name.endswith('running_mean') or (name.endswith('bias') and name[:-4] + 'running_var' in shapes):
+            out[name] = (0.2 * torch.randn(shape, generator=g, dtype=torch.float64)).to(dtype)
+            continue
         if 'layer_norm' in name:
             out[name] = torch.ones(shape, dtype=dtype) if name.endswith('weight') else torch.zeros(shape, dtype=dtype)
             continue

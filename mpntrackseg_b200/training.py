@@ -105,6 +105,13 @@ class CoreTrainer:
 
     def __init__(self, model, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8):
         self.model = model
+        from .models.mlp import MLP
+        for name, mod in model.named_modules():
+            if isinstance(mod, MLP) and name.startswith(CORE_PREFIXES) and (mod.use_batchnorm or mod.dropout_p != 0):
+                raise NotImplementedError(f'{name}: BatchNorm / Dropout are not built into the training kernels '
+                                          '(the shipped configs train with use_batchnorm: False, dropout_p: 0)')
+        if model.MPNet.node_model.node_agg_fn != 'sum':
+            raise NotImplementedError("training kernels are built for node_agg_fn = 'sum'")
         self.named = OrderedDict((n, p) for n, p in model.named_parameters() if n.startswith(CORE_PREFIXES))
         dev = next(iter(self.named.values())).device
         total = sum(p.numel() for p in self.named.values())
@@ -163,7 +170,7 @@ class CoreTrainer:
         ptr_c = torch.zeros(n + 1, dtype=torch.int32, device=pooled.device)
         ptr_c[1:] = torch.cumsum(torch.bincount(scol.long(), minlength=n), 0).to(torch.int32)
         dev = pooled.device
-        steps, first_cls = m.num_enc_steps, m.num_enc_steps - m.num_class_steps + 1
+        steps, first_cls = m.num_enc_steps, max(m.num_enc_steps - m.num_class_steps + 1, 1)
         n_out = lay.num_out
 
         enc_n, enc_e = self._mlp('encoder.node_model'), self._mlp('encoder.edge_model')
@@ -171,6 +178,9 @@ class CoreTrainer:
         flow = {'out': self._mlp('MPNet.node_model.flow_out_model'), 'in': self._mlp('MPNet.node_model.flow_in_model')}
         node_lin = self._lin('MPNet.node_model.node_model', 0, True)
         cls = self._mlp('classifier.edge_model')
+        for what, mlp_ in (('edge model', edge_mlp), ('flow_out model', flow['out']), ('flow_in model', flow['in']), ('classifier', cls)):
+            if len(mlp_) != 2:
+                raise NotImplementedError(f'the training kernels expect two-layer MLPs; the {what} has {len(mlp_)} layers')
         dn, de = node_lin.w.shape[0], edge_mlp[-1].w.shape[0]
         fh = flow['out'][0].w.shape[0]
 

@@ -39,11 +39,17 @@ def _linear_slots(P, prefix):
 
 
 def mlp(P, prefix, h):
-    """Linear -> ReLU per layer; a layer whose width is 1 gets no ReLU.
-    reference: models/mlp.py:12-23 (batch-norm / dropout off as in every shipped config)"""
+    """Linear [-> BatchNorm1d (evaluation mode: running statistics)] -> ReLU per layer; a layer whose width is 1 is a
+    bare Linear; Dropout is the identity in evaluation mode.  reference: models/mlp.py:12-23"""
     for s in _linear_slots(P, prefix):
         w, b = P[f'{prefix}.fc_layers.{s}.weight'], P[f'{prefix}.fc_layers.{s}.bias']
+        if w.dim() != 2:
+            continue                                   # a BatchNorm1d weight vector, handled with its Linear
         h = F.linear(h, w, b)
+        bn = f'{prefix}.fc_layers.{s + 1}'
+        if w.shape[0] != 1 and f'{bn}.running_mean' in P:
+            h = F.batch_norm(h, P[f'{bn}.running_mean'], P[f'{bn}.running_var'], P[f'{bn}.weight'], P[f'{bn}.bias'],
+                             training=False, eps=1e-5)
         if w.shape[0] != 1:
             h = F.relu(h)
     return h

@@ -23,12 +23,34 @@ CASES = {
     'kitti_shape': dict(win=dict(T=20, D=8, k=100, seed=2, node_feats='pooled'),
                         ds=dict(top_k_nns=100, frames_per_graph=20), steps=(12, 11), wseed=6,
                         gain=0.95),
+    # non-default model options (models/mpn.py:263-273 node_agg_fn; models/mlp.py:14-21 BatchNorm1d / Dropout, eval mode)
+    'tiny_mean': dict(win=dict(T=6, D=7, k=5, seed=14, node_feats='pooled'), ds=dict(top_k_nns=5, frames_per_graph=6),
+                      steps=(4, 3), wseed=9, gain=2.6, model=dict(node_agg_fn='mean')),
+    'tiny_max': dict(win=dict(T=6, D=7, k=5, seed=15, node_feats='pooled'), ds=dict(top_k_nns=5, frames_per_graph=6),
+                     steps=(4, 3), wseed=10, gain=2.6, model=dict(node_agg_fn='max')),
+    'tiny_bn': dict(win=dict(T=6, D=7, k=5, seed=16, node_feats='pooled'), ds=dict(top_k_nns=5, frames_per_graph=6),
+                    steps=(4, 3), wseed=11, gain=2.0, model=dict(batchnorm=True, dropout_p=0.3)),
     'steps0': dict(win=dict(T=4, D=6, k=4, seed=13, node_feats='pooled'),
                    ds=dict(top_k_nns=4, frames_per_graph=4), steps=(0, 0), wseed=7, gain=1.0),
 }
 
 TRACKER_CASE = dict(win=dict(T=9, D=9, k=7, seed=21, node_feats='pooled'),
                     ds=dict(top_k_nns=7, frames_per_graph=5), steps=(4, 3), wseed=8, gain=2.2)
+
+
+def case_model_params(c):
+    """graph_model_params of a case: the shipped widths with the case's step counts and option overrides."""
+    from mpntrackseg_b200.config import default_graph_model_params
+    mp = default_graph_model_params(*c['steps'])
+    over = c.get('model', {})
+    if 'node_agg_fn' in over:
+        mp['node_agg_fn'] = over['node_agg_fn']
+    for k in ('encoder_feats_dict', 'edge_model_feats_dict', 'node_model_feats_dict', 'classifier_feats_dict'):
+        if over.get('batchnorm'):
+            mp[k]['use_batchnorm'] = True
+        if 'dropout_p' in over:
+            mp[k]['dropout_p'] = over['dropout_p']
+    return mp
 
 
 def checksum(*tensors):
@@ -48,7 +70,7 @@ def load_case(name):
     assert checksum(win.frame, win.reid, win.x, win.bb_height, win.feet_x) == str(gold['input_checksum']), \
         'seeded inputs differ from the ones the fixture was generated with'
     ds = default_dataset_params(**c['ds'])
-    mp = default_graph_model_params(*c['steps'])
+    mp = case_model_params(c)
     P = synth.make_params(mp, seed=c['wseed'], gain=c['gain'])
     key = [k for k in P if k.startswith('classifier.edge_model') and k.endswith('bias')][-1]
     P[key] = P[key] - float(gold['bias_shift'])

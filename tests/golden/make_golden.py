@@ -35,7 +35,7 @@ from mot_neural_solver.utils.graph import (  # noqa: E402
 from mpntrackseg_b200 import synth  # noqa: E402
 from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params  # noqa: E402
 
-from cases import CASES, TRACKER_CASE, checksum  # noqa: E402
+from cases import CASES, TRACKER_CASE, case_model_params, checksum  # noqa: E402
 
 
 def det_df(win):
@@ -114,7 +114,7 @@ class Data:
 def run_case(name, c):
     win = synth.make_window(**c['win'])
     ds = default_dataset_params(**c['ds'])
-    mp = default_graph_model_params(*c['steps'])
+    mp = case_model_params(c)
     mfd = c.get('max_frame_dist', 'max')
     n_cand, edge_index, edge_attr, _ = ref_build_graph(win, ds, False, mfd)
     data = Data()
