@@ -34,6 +34,13 @@ CASES = {
                    ds=dict(top_k_nns=4, frames_per_graph=4), steps=(0, 0), wseed=7, gain=1.0),
 }
 
+# large cases, fixtures hold a reduced set of outputs (see make_golden.run_config5_case / run_big_window_case)
+BIG_CASES = {
+    'config5': dict(win=dict(T=15, D=300, k=100, seed=5, node_feats='pooled', node_dim=2048, min_gap=2e-6), ds=dict(top_k_nns=100, frames_per_graph=15),
+                    steps=(12, 11), wseed=12, gain=1.15),
+    'big_window': dict(win=dict(T=15, D=360, k=20, seed=6, node_feats='pooled', node_dim=8, min_gap=2e-6), ds=dict(top_k_nns=20, frames_per_graph=15)),
+}
+
 TRACKER_CASE = dict(win=dict(T=9, D=9, k=7, seed=21, node_feats='pooled'),
                     ds=dict(top_k_nns=7, frames_per_graph=5), steps=(4, 3), wseed=8, gain=2.2)
 
@@ -77,3 +84,25 @@ def load_case(name):
     assert checksum(*P.values()) == str(gold['param_checksum'])
     return dict(case=c, win=win, ds=ds, mp=mp, P=P, gold=gold,
                 max_frame_dist=c.get('max_frame_dist', 'max'))
+
+
+def load_big_case(name):
+    """Seeded inputs (and weights) of a BIG_CASES entry + its reduced reference outputs."""
+    from mpntrackseg_b200 import synth
+    from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params
+    c = BIG_CASES[name]
+    gold = dict(np.load(os.path.join(HERE, f'{name}.npz')))
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    out = dict(case=c, win=win, ds=ds, gold=gold)
+    if 'steps' in c:
+        assert checksum(win.frame, win.reid, win.x, win.bb_height, win.feet_x) == str(gold['input_checksum'])
+        mp = default_graph_model_params(*c['steps'])
+        P = synth.make_params(mp, seed=c['wseed'], gain=c['gain'])
+        key = [k for k in P if k.startswith('classifier.edge_model') and k.endswith('bias')][-1]
+        P[key] = P[key] - float(gold['bias_shift'])
+        assert checksum(*P.values()) == str(gold['param_checksum'])
+        out.update(mp=mp, P=P)
+    else:
+        assert checksum(win.frame, win.reid, win.bb_height, win.feet_x) == str(gold['input_checksum'])
+    return out

@@ -35,7 +35,7 @@ from mot_neural_solver.utils.graph import (  # noqa: E402
 from mpntrackseg_b200 import synth  # noqa: E402
 from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params  # noqa: E402
 
-from cases import CASES, TRACKER_CASE, case_model_params, checksum  # noqa: E402
+from cases import BIG_CASES, CASES, TRACKER_CASE, case_model_params, checksum  # noqa: E402
 
 
 def det_df(win):
@@ -301,6 +301,62 @@ def run_tracker_sequence_case():
                         input_checksum=gold_w['input_checksum'], param_checksum=gold_w['param_checksum'])
 
 
+def ref_build_graph_chunked(win, ds):
+    """ref_build_graph for windows whose 9-14 M candidate pairs do not fit an un-chunked gather: the pair distances are
+    evaluated in chunks of 50 000 (the reference's own inference-mode loop, data/mot_graph.py:299-303; a pair's distance
+    does not depend on its chunk)."""
+    edge_ixs = get_time_valid_conn_ixs(frame_num=win.frame, max_frame_dist='max', use_cuda=False)
+    n_cand = edge_ixs.shape[1]
+    d = torch.cat([F.pairwise_distance(win.reid[edge_ixs[0][i:i + 50000]], win.reid[edge_ixs[1][i:i + 50000]])
+                   for i in range(0, n_cand, 50000)])
+    keep = get_knn_mask(pwise_dist=d, edge_ixs=edge_ixs, num_nodes=win.N, top_k_nns=ds['top_k_nns'],
+                        reciprocal_k_nns=ds['reciprocal_k_nns'], symmetric_edges=False, use_cuda=False)
+    edge_ixs, d = edge_ixs.T[keep].T, d[keep]
+    fd = compute_edge_feats_dict(edge_ixs=edge_ixs, det_df=det_df(win), fps=win.fps, use_cuda=False)
+    feats = torch.stack([fd[n] for n in ds['edge_feats_to_use'] if n in fd]).T
+    feats = torch.cat((feats, d.view(-1, 1)), dim=1)
+    return n_cand, torch.cat((edge_ixs, torch.stack((edge_ixs[1], edge_ixs[0]))), dim=1), torch.cat((feats, feats), dim=0)
+
+
+def run_config5_case():
+    """BASELINE.json configs[4]: dense crowd window, 15 frames x 300 detections, k = 100 (N = 4,500, E ~ 195 k).  The
+    fixture keeps the edge list, a strided sample of the edge features and the logits of the last step (+ per-step
+    means), not all 11 x E logits."""
+    c = BIG_CASES['config5']
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    mp = default_graph_model_params(*c['steps'])
+    n_cand, edge_index, edge_attr = ref_build_graph_chunked(win, ds)
+    data = Data()
+    data.x, data.edge_index, data.edge_attr, data.x_ext = win.x, edge_index, edge_attr, None
+    model = RefMOTMPNet(mp).eval()
+    P, shift = centred_params(mp, c['wseed'], c['gain'], model, data)
+    with torch.no_grad():
+        core = core_forward(model, data)
+    logits = torch.stack([t.view(-1) for t in core['classified_edges']])
+    print('config5', dict(N=win.N, E=edge_index.shape[1], cand=n_cand, logit_std=float(logits[-1].std()),
+                          frac_pos=float((logits[-1] > 0).float().mean()), node_max=float(core['node_state'].max())))
+    np.savez_compressed(os.path.join(HERE, 'config5.npz'), n_candidates=np.int64(n_cand),
+                        edge_index=edge_index.numpy().astype(np.int32), edge_attr_sample=edge_attr[::16].numpy(),
+                        logits_last=logits[-1].numpy(), logits_first=logits[0].numpy(),
+                        logits_step_means=logits.double().mean(dim=1).numpy(), bias_shift=np.float64(shift),
+                        input_checksum=checksum(win.frame, win.reid, win.x, win.bb_height, win.feet_x),
+                        param_checksum=checksum(*P.values()))
+
+
+def run_big_window_case():
+    """A window of 5,400 detections (> 5,120: the batched builder's general select path): kept pairs only."""
+    c = BIG_CASES['big_window']
+    win = synth.make_window(**c['win'])
+    ds = default_dataset_params(**c['ds'])
+    n_cand, edge_index, edge_attr = ref_build_graph_chunked(win, ds)
+    p = edge_index.shape[1] // 2
+    print('big_window', dict(N=win.N, pairs=p, cand=n_cand))
+    np.savez_compressed(os.path.join(HERE, 'big_window.npz'), n_candidates=np.int64(n_cand),
+                        pairs=edge_index[:, :p].numpy().astype(np.int32), reid_dist_sample=edge_attr[:p:8, 5].numpy(),
+                        input_checksum=checksum(win.frame, win.reid, win.bb_height, win.feet_x))
+
+
 def _reference_function(path, name, glob):
     """Compile ONE function of a reference module that cannot be imported here (its module imports packages that
     are absent) straight from the reference's source file; nothing is copied into the repo."""
@@ -362,3 +418,7 @@ if __name__ == '__main__':
         run_edge_labels_case()
     if not only or 'embedding_store' in only:
         run_embedding_store_case()
+    if 'config5' in only:                       # minutes of CPU time each: only on request
+        run_config5_case()
+    if 'big_window' in only:
+        run_big_window_case()

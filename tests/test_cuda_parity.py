@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import CASES, load_case
+from cases import CASES, load_big_case, load_case
 from mpntrackseg_b200 import synth
 from mpntrackseg_b200.config import default_dataset_params, default_graph_model_params
 from oracle import graph_ref, mpn_ref
@@ -906,3 +906,52 @@ def test_embedding_store_pool_and_motgraph_from_store(tmp_path):
         with torch.no_grad():
             a_, b_ = model(g)['classified_edges'][-1], model(g_ref)['classified_edges'][-1]
         assert torch.equal(a_, b_) if exact else torch.allclose(a_, b_)
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_config5_dense_crowd_window_matches_reference_golden(engine):
+    """BASELINE.json configs[4] (15 frames x 300 detections, k = 100; N = 4,500, E = 179 k, node state 4.8e4): graph
+    build bit-exact, logits within the bar, against outputs of the reference itself (tests/golden/config5.npz)."""
+    from mpntrackseg_b200.data.mot_graph import MOTGraph, build_window_graphs
+    c = load_big_case('config5')
+    win, ds, gold = c['win'], c['ds'], c['gold']
+    g = MOTGraph.from_tensors(synth.det_columns(win), win.reid, win.x, None, {'fps': win.fps}, ds).construct_graph_object()
+    assert np.array_equal(g.edge_index.cpu().numpy(), gold['edge_index'].astype(np.int64))
+    np.testing.assert_allclose(g.edge_attr[::16].cpu().numpy(), gold['edge_attr_sample'], rtol=2e-6, atol=2e-7)
+    tab = {k: torch.from_numpy(v) for k, v in synth.det_columns(win).items()}
+    tab.update(reid=win.reid, x=win.x.to(dev()))
+    batch = build_window_graphs([tab], ds, win.fps, device=dev(), engine=engine)         # the batched (Gram) builder
+    assert torch.equal(batch.edge_index, g.edge_index)
+    model = make_model(c['mp'], c['P'], engine)
+    with torch.no_grad():
+        out = model(g)
+    lg = [t.view(-1).cpu().numpy() for t in out['classified_edges']]
+    assert_logits_close(lg[-1], gold['logits_last'], 'config5 last step')
+    assert_logits_close(lg[0], gold['logits_first'], 'config5 first classified step')
+    np.testing.assert_allclose(np.array([float(np.mean(v.astype(np.float64))) for v in lg]), gold['logits_step_means'],
+                               rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_window_beyond_5120_nodes_takes_the_general_select_path(engine):
+    """A window of 5,400 detections is above the fused row-select limit (5,120): batch_row_kth_kernel / knn_pairs_kernel
+    (csrc/knn_graph.cu) must produce the reference's kept pairs (tests/golden/big_window.npz), alone and next to a
+    small window in the same batch."""
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    c = load_big_case('big_window')
+    win, ds, gold = c['win'], c['ds'], c['gold']
+    tab = {k: torch.from_numpy(v) for k, v in synth.det_columns(win).items()}
+    tab.update(reid=win.reid, x=win.x.to(dev()))
+    small = synth.make_window(T=6, D=9, k=20, seed=3, node_feats='pooled', node_dim=8)
+    stab = {k: torch.from_numpy(v) for k, v in synth.det_columns(small).items()}
+    stab.update(reid=small.reid, x=small.x.to(dev()))
+    ref_small = graph_ref.build_graph(small.frame, small.reid, synth.det_columns(small), small.fps, ds)
+    for tabs in ([tab], [stab, tab]):
+        batch = build_window_graphs(tabs, ds, win.fps, device=dev(), engine=engine)
+        gi = len(tabs) - 1
+        g = batch.graph(gi)
+        p = g.edge_index.shape[1] // 2
+        assert np.array_equal(g.edge_index[:, :p].cpu().numpy(), gold['pairs'].astype(np.int64))
+        np.testing.assert_allclose(g.edge_attr[:p:8, 5].cpu().numpy(), gold['reid_dist_sample'], rtol=2e-6)
+        if gi:
+            assert torch.equal(batch.graph(0).edge_index.cpu(), ref_small['edge_index'])
