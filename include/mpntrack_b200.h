@@ -291,6 +291,36 @@ int mpn_mp_forward_tc(const mpn_core_weights* h_w, const mpn_edge_layout* h_g, c
                       void* workspace, float* logits, float* x_out, float* e_out, int32_t* status,
                       void* stream);
 
+/* ------------------------------------------------------------------ rounding and identity assignment (after the path)
+ * The sequence graph at this point is the undirected, pruned graph of utils/graph.py:165-207: one entry per pair,
+ * row = earlier node.  Integer / comparison work only; results are deterministic and equal the reference's. */
+
+/* utils/evaluation.py:370-414 compute_constr_satisfaction_rate: flow_out[v] = sum of edges_out over edges leaving v
+ * (row == v), flow_in[v] over edges entering v (col == v), divided by 2 when undirected_edges != 0 (every pair stored
+ * in both directions; pairs are then ordered here).  edges_out must be BINARISED (exactly 0 or 1; MPN_EINVAL otherwise).
+ * flow_in / flow_out [N] may be NULL.  h_counts (host) = {#nodes with flow_in > 1, #nodes with flow_out > 1,
+ * #constraints = #distinct rows + #distinct cols}; the rate is 1 - (h[0] + h[1]) / h[2].  SYNCS.
+ * workspace: mpn_rounding_workspace(N) bytes. */
+int64_t mpn_rounding_workspace(int64_t num_nodes);
+int mpn_constr_satisfaction(const int64_t* row, const int64_t* col, const float* edges_out, int64_t num_edges,
+                            int64_t num_nodes, int undirected_edges, void* workspace, float* flow_in, float* flow_out,
+                            int64_t* h_counts /*[3]*/, void* stream);
+
+/* tracker/projectors.py:11-67 GreedyProjector.project: round_preds = edge_preds > 0.5, then every violated outgoing
+ * constraint (flow_out > 1), and after those every still-violated incoming one, keeps its active edge with the largest
+ * prediction (the first one on ties) and switches the others off.  h_counts as above, for the INITIAL rounding
+ * (projectors.py:22-25).  On return no node has more than one active edge per direction.  SYNCS. */
+int mpn_greedy_project(const int64_t* row, const int64_t* col, const float* edge_preds, int64_t num_edges,
+                       int64_t num_nodes, void* workspace, float* round_preds, int64_t* h_counts /*[3]*/, void* stream);
+
+/* tracker/mpn_tracker.py:231-248 _assign_ped_ids: labels[v] = index of v's connected component in the graph of the
+ * edges with edge_vals == 1, components numbered by their smallest node (scipy.sparse.csgraph.connected_components,
+ * directed=False).  *h_num_components: number of components.  SYNCS.
+ * workspace: mpn_connected_components_workspace(N) bytes. */
+int64_t mpn_connected_components_workspace(int64_t num_nodes);
+int mpn_connected_components(const int64_t* row, const int64_t* col, const float* edge_vals, int64_t num_edges,
+                             int64_t num_nodes, void* workspace, int64_t* labels, int64_t* h_num_components, void* stream);
+
 /* Diagnostics of the last mpn_mp_forward_tc run on `workspace` (same n, e): the scale exponents s_t and the maxima
  * they were derived from, entries [0, num_steps + 2) indexed by step (1-based).  h_* are HOST arrays and may be
  * NULL.  SYNCS. */

@@ -76,6 +76,11 @@ SIGNATURES = {
     'mpn_weighted_bce': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_attn_aggregate': (C.c_int, [c_vp, c_i64, c_i64, C.POINTER(EdgeLayout), c_vp, c_vp, c_vp, c_vp]),
     'mpn_mp_tc_workspace': (c_i64, [c_i64, c_i64]),
+    'mpn_rounding_workspace': (c_i64, [c_i64]),
+    'mpn_constr_satisfaction': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64p, c_vp]),
+    'mpn_greedy_project': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64p, c_vp]),
+    'mpn_connected_components_workspace': (c_i64, [c_i64]),
+    'mpn_connected_components': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64p, c_vp]),
     'mpn_mp_tc_read_schedule': (C.c_int, [c_vp, c_i64, c_i64, c_i32, C.POINTER(c_i32), C.POINTER(c_f32), C.POINTER(c_f32), c_vp]),
     'mpn_mp_forward_tc': (C.c_int, [C.POINTER(CoreWeights), C.POINTER(EdgeLayout), c_vp, c_vp, c_i32, c_i32,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -429,3 +429,49 @@ def weighted_bce(logits, labels, weight=1.0, want_grad=False):
     check(lib().mpn_weighted_bce(ptr(lg), ptr(lb), s, e, float(weight), ptr(ws), ptr(loss), ptr(pw), ptr(grad),
                                  stream_ptr()), 'weighted_bce')
     return (loss, pw, grad) if want_grad else (loss, pw)
+
+
+# ------------------------------------------------------------------ rounding / identities
+def _rate(counts):
+    """1 - violated / constraints in float32, as the reference's tensor arithmetic (evaluation.py:404-409)."""
+    viol = torch.tensor(float(counts[0] + counts[1]), dtype=torch.float32)
+    return float((1 - viol / int(counts[2])).item()) if counts[2] else float('nan')
+
+
+def constr_satisfaction(edge_index, edges_out, num_nodes, undirected_edges=True):
+    """(rate, flow_in [N], flow_out [N]) of BINARISED edge values.  utils/evaluation.py:370-414"""
+    ei = _req(edge_index, torch.int64, 'edge_index')
+    v = _req(edges_out.reshape(-1), torch.float32, 'edges_out')
+    e, n = ei.shape[1], int(num_nodes)
+    ws = _bytes(lib().mpn_rounding_workspace(n), ei.device)
+    fin = torch.empty(n, dtype=torch.float32, device=ei.device)
+    fout = torch.empty(n, dtype=torch.float32, device=ei.device)
+    counts = (C.c_int64 * 3)()
+    check(lib().mpn_constr_satisfaction(ptr(ei[0]), ptr(ei[1]), ptr(v), e, n, int(bool(undirected_edges)), ptr(ws), ptr(fin),
+                                        ptr(fout), counts, stream_ptr()), 'constr_satisfaction')
+    return _rate(counts), fin, fout
+
+
+def greedy_project(edge_index, edge_preds, num_nodes):
+    """(round_preds [E] float 0/1, constraint satisfaction rate of the plain > 0.5 rounding).  tracker/projectors.py:11-67"""
+    ei = _req(edge_index, torch.int64, 'edge_index')
+    p = _req(edge_preds.reshape(-1), torch.float32, 'edge_preds')
+    e, n = ei.shape[1], int(num_nodes)
+    ws = _bytes(lib().mpn_rounding_workspace(n), ei.device)
+    out = torch.empty(e, dtype=torch.float32, device=ei.device)
+    counts = (C.c_int64 * 3)()
+    check(lib().mpn_greedy_project(ptr(ei[0]), ptr(ei[1]), ptr(p), e, n, ptr(ws), ptr(out), counts, stream_ptr()), 'greedy_project')
+    return out, _rate(counts)
+
+
+def connected_components(edge_index, edge_vals, num_nodes):
+    """(labels [N] int64, number of components) over the edges with value 1.  tracker/mpn_tracker.py:231-248"""
+    ei = _req(edge_index, torch.int64, 'edge_index')
+    v = _req(edge_vals.reshape(-1), torch.float32, 'edge_vals')
+    e, n = ei.shape[1], int(num_nodes)
+    ws = _bytes(lib().mpn_connected_components_workspace(n), ei.device)
+    labels = torch.empty(n, dtype=torch.int64, device=ei.device)
+    ncomp = C.c_int64(0)
+    check(lib().mpn_connected_components(ptr(ei[0]), ptr(ei[1]), ptr(v), e, n, ptr(ws), ptr(labels), C.byref(ncomp), stream_ptr()),
+          'connected_components')
+    return labels, ncomp.value

@@ -282,3 +282,33 @@ class MPNTracker(object):
         final = total / count
         final[torch.isnan(final)] = 0
         go.edge_preds = final
+
+    # ------------------------------------------------------------------ rounding + identities
+    def _project_graph_model_output(self):
+        """Rounds the edge predictions of the (undirected, pruned) sequence graph into a feasible flow on the GPU.
+        reference: tracker/mpn_tracker.py:212-229 -- except that the graph stays on the device (the reference turns
+        it into numpy here); ``constr_satisf_rate`` is set on ``full_graph`` as there."""
+        from .projectors import ExactProjector, GreedyProjector
+        method = self.eval_params['rounding_method']
+        if method == 'greedy':
+            projector = GreedyProjector(self.full_graph)
+        elif method == 'exact':
+            projector = ExactProjector(self.full_graph, solver_backend=self.eval_params.get('solver_backend', 'pulp'))
+        else:
+            raise RuntimeError("Rounding type for projector not understood")
+        projector.project()
+        self.full_graph.constr_satisf_rate = projector.constr_satisf_rate
+
+    def _assign_ped_ids(self):
+        """One identity per connected component of the active edges (tracker/mpn_tracker.py:231-248; the reference
+        calls scipy's connected_components on the host).  Returns the [N] int64 labels on the device; when the sequence
+        graph carries a ``graph_df`` they are also stored as its ``ped_id`` column (one device -> host copy)."""
+        from .. import ops
+        go = self.full_graph.graph_obj
+        labels, _ = ops.connected_components(go.edge_index, (go.edge_preds == 1).float(), go.num_nodes)
+        df = getattr(self.full_graph, 'graph_df', None)
+        if df is not None and hasattr(df, 'copy') and not isinstance(df, dict):
+            assert len(labels) == df.shape[0], "Ped Ids Label format is wrong"
+            self.final_projected_output = df.copy()
+            self.final_projected_output['ped_id'] = labels.cpu().numpy()
+        return labels

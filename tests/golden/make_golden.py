@@ -368,6 +368,65 @@ def _reference_function(path, name, glob):
     return glob[name]
 
 
+def _reference_class(path, name, glob):
+    import ast
+    src = open(path).read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == name)
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, 'exec'), glob)
+    return glob[name]
+
+
+def run_rounding_case():
+    """Rounding + identity assignment by the reference's own code on seeded sequence graphs:
+    compute_constr_satisfaction_rate (utils/evaluation.py:370-414) and GreedyProjector (tracker/projectors.py:11-67)
+    are compiled from their files (the modules import motmetrics / pulp, absent here) with the torch_scatter stand-in;
+    the identities come from scipy's connected_components as in tracker/mpn_tracker.py:231-248."""
+    from types import SimpleNamespace
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    from torch_scatter import scatter_add
+    csr = _reference_function('/root/reference/src/mot_neural_solver/utils/evaluation.py', 'compute_constr_satisfaction_rate',
+                              {'torch': torch, 'scatter_add': scatter_add})
+    Greedy = _reference_class('/root/reference/src/mot_neural_solver/tracker/projectors.py', 'GreedyProjector',
+                              {'torch': torch, 'scatter_add': scatter_add, 'compute_constr_satisfaction_rate': csr})
+    out = {}
+    for tag, (T, D, seed, p_link, p_noise) in {'a': (12, 9, 51, 0.9, 0.12), 'b': (30, 25, 52, 0.8, 0.05)}.items():
+        g = torch.Generator().manual_seed(seed)
+        n = T * D
+        frame = torch.arange(T).repeat_interleave(D)
+        ident = torch.arange(D).repeat(T)
+        ii, jj = torch.triu_indices(n, n, offset=1)
+        ok = (frame[jj] > frame[ii]) & (frame[jj] - frame[ii] <= 3)
+        ii, jj = ii[ok], jj[ok]
+        same = (ident[ii] == ident[jj]) & (frame[jj] - frame[ii] == 1)
+        u = torch.rand(ii.numel(), generator=g)
+        preds = torch.where(same, 0.55 + 0.45 * torch.rand(ii.numel(), generator=g), 0.5 * torch.rand(ii.numel(), generator=g))
+        preds = torch.where(same & (u > p_link), 0.3 * torch.rand(ii.numel(), generator=g), preds)          # missed links
+        preds = torch.where(~same & (u < p_noise), 0.5 + 0.5 * torch.rand(ii.numel(), generator=g), preds)  # spurious links
+        preds[::7] = preds[::7].round(decimals=1)                                                             # exact ties
+        keep = preds > 0.05                                                                                  # a pruned edge list
+        edge_index, preds = torch.stack((ii[keep], jj[keep])), preds[keep].float()
+        graph_obj = SimpleNamespace(edge_index=edge_index, edge_preds=preds.clone(), num_nodes=n)
+        rounded0 = (preds > 0.5).float()
+        rate_u, fin_u, fout_u = csr(graph_obj=SimpleNamespace(edge_index=torch.cat((edge_index, edge_index.flip(0)), dim=1),
+                                                              num_nodes=n),
+                                    edges_out=torch.cat((rounded0, rounded0)), undirected_edges=True, return_flow_vals=True)
+        proj = Greedy(SimpleNamespace(graph_obj=graph_obj))
+        proj.project()
+        final = graph_obj.edge_preds
+        mask = (final == 1).numpy()
+        nz = edge_index.numpy()[:, mask]
+        ncomp, labels = connected_components(csgraph=csr_matrix((final.numpy()[mask].astype(int), (tuple(nz))), shape=(n, n)),
+                                             directed=False, return_labels=True)
+        print('rounding', tag, dict(N=n, E=edge_index.shape[1], on=int(rounded0.sum()), kept=int(final.sum()),
+                                    rate=proj.constr_satisf_rate, comps=ncomp))
+        out.update({f'edge_index_{tag}': edge_index.numpy().astype(np.int32), f'preds_{tag}': preds.numpy(),
+                    f'round_{tag}': final.numpy(), f'rate_{tag}': np.float64(proj.constr_satisf_rate),
+                    f'rate_undirected_{tag}': np.float64(rate_u), f'flow_in_{tag}': fin_u.numpy(), f'flow_out_{tag}': fout_u.numpy(),
+                    f'labels_{tag}': labels.astype(np.int64), f'ncomp_{tag}': np.int64(ncomp), f'n_{tag}': np.int64(n)})
+    np.savez_compressed(os.path.join(HERE, 'rounding.npz'), **out)
+
+
 def run_embedding_store_case():
     """Per-frame embedding files in the layout the reference's preprocessing writes, read back by the reference's
     own ``load_precomputed_embeddings`` (utils/rgb.py:150-188; utils/rgb.py itself needs skimage / pycocotools, so
@@ -418,6 +477,8 @@ if __name__ == '__main__':
         run_edge_labels_case()
     if not only or 'embedding_store' in only:
         run_embedding_store_case()
+    if not only or 'rounding' in only:
+        run_rounding_case()
     if 'config5' in only:                       # minutes of CPU time each: only on request
         run_config5_case()
     if 'big_window' in only:

@@ -955,3 +955,49 @@ def test_window_beyond_5120_nodes_takes_the_general_select_path(engine):
         np.testing.assert_allclose(g.edge_attr[:p:8, 5].cpu().numpy(), gold['reid_dist_sample'], rtol=2e-6)
         if gi:
             assert torch.equal(batch.graph(0).edge_index.cpu(), ref_small['edge_index'])
+
+
+# ------------------------------------------------------------------ rounding + identity assignment
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_rounding_and_identities_match_the_reference(tag):
+    """Greedy projection, constraint statistics and connected components against outputs of the reference's own
+    GreedyProjector / compute_constr_satisfaction_rate and scipy's connected_components (tests/golden/rounding.npz):
+    integer work, so everything is bit-exact."""
+    import os
+    from types import SimpleNamespace
+    from mpntrackseg_b200 import ops
+    from mpntrackseg_b200.data.mot_graph import Graph
+    from mpntrackseg_b200.tracker.mpn_tracker import MPNTracker
+    from mpntrackseg_b200.utils.evaluation import compute_constr_satisfaction_rate
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rounding.npz')))
+    n = int(gold[f'n_{tag}'])
+    ei = torch.from_numpy(gold[f'edge_index_{tag}'].astype(np.int64)).to(dev())
+    preds = torch.from_numpy(gold[f'preds_{tag}']).to(dev())
+    go = Graph(x=torch.zeros(n, 1, device=dev()), edge_index=ei, edge_preds=preds.clone())
+    # statistics of the plain rounding on the both-directions edge list (undirected_edges=True)
+    r0 = (preds > 0.5).float()
+    both = Graph(x=go.x, edge_index=torch.cat((ei, ei.flip(0)), dim=1))
+    rate_u, fin, fout = compute_constr_satisfaction_rate(both, torch.cat((r0, r0)), undirected_edges=True, return_flow_vals=True)
+    assert rate_u == float(gold[f'rate_undirected_{tag}'])
+    assert np.array_equal(fin.cpu().numpy(), gold[f'flow_in_{tag}']) and np.array_equal(fout.cpu().numpy(), gold[f'flow_out_{tag}'])
+    with pytest.raises(ValueError):
+        compute_constr_satisfaction_rate(go, preds, undirected_edges=False)             # not binarised
+    # the tracker's two steps
+    tr = MPNTracker(eval_params={'rounding_method': 'greedy'})
+    tr.full_graph = SimpleNamespace(graph_obj=go)
+    tr._project_graph_model_output()
+    assert tr.full_graph.constr_satisf_rate == float(gold[f'rate_{tag}'])
+    assert np.array_equal(go.edge_preds.cpu().numpy(), gold[f'round_{tag}'])
+    rate_after, fin, fout = compute_constr_satisfaction_rate(go, go.edge_preds, undirected_edges=False, return_flow_vals=True)
+    assert rate_after == 1.0 and float(fin.max()) <= 1 and float(fout.max()) <= 1
+    labels = tr._assign_ped_ids()
+    assert np.array_equal(labels.cpu().numpy(), gold[f'labels_{tag}'])
+    # components of an arbitrary (not path-shaped) edge set, shuffled edge order
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(3)).to(dev())
+    lab2, ncomp = ops.connected_components(ei[:, perm], r0[perm], n)
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    m = r0.cpu().numpy() == 1
+    ref_n, ref_l = connected_components(csr_matrix((np.ones(int(m.sum()), dtype=int), tuple(ei.cpu().numpy()[:, m])), shape=(n, n)),
+                                        directed=False, return_labels=True)
+    assert ncomp == ref_n and np.array_equal(lab2.cpu().numpy(), ref_l)
