@@ -276,6 +276,12 @@ int mpn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   void* stream);
 
+/* The same Adam step with the step number kept on the device: *d_step (int64) is incremented first, then used for the
+ * bias corrections, so that a captured CUDA graph of a whole training step can be replayed. */
+int mpn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t* d_step, float grad_scale,
+                      void* stream);
+
 /* Same contract as mpn_mp_forward (1 <= num_steps <= 1000), evaluated on the tcgen05 tensor cores:
  * per 128-edge tile the four dense layers run as kind::f16 MMAs with fp16 hi/lo split operands
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~22 significant bits per operand).

@@ -72,6 +72,7 @@ SIGNATURES = {
     'mpn_segment_sum': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_i64, c_vp]),
     'mpn_relu_mask': (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     'mpn_adam_step': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
+    'mpn_adam_step_dev': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32, c_vp]),
     'mpn_weighted_bce_workspace': (c_i64, []),
     'mpn_weighted_bce': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_attn_aggregate': (C.c_int, [c_vp, c_i64, c_i64, C.POINTER(EdgeLayout), c_vp, c_vp, c_vp, c_vp]),

@@ -162,6 +162,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// step counter on the device (CUDA-graph replays of a training step must not bake the step number in)
+__global__ void bump_step_kernel(int64_t* step) { *step += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                const int64_t* __restrict__ step, float grad_scale) {
+  const float t = (float)*step;
+  const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale + weight_decay * p[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
 static void keep_async_pool() {
   static bool done = false;
   if (done) return;
@@ -279,6 +296,20 @@ int mpn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   adam_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                           weight_decay, bc1, bc2, grad_scale);
   count_launch();
+  MPN_LAUNCH_CHECK();
+  return MPN_OK;
+}
+
+int mpn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int64_t* d_step, float grad_scale, void* stream) {
+  MPN_CHECK_ARG(d_step != nullptr, "adam_step_dev: null step counter");
+  bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(d_step); count_launch();
+  if (n > 0) {
+    MPN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "adam_step_dev: bad arguments");
+    adam_dev_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                weight_decay, d_step, grad_scale);
+    count_launch();
+  }
   MPN_LAUNCH_CHECK();
   return MPN_OK;
 }

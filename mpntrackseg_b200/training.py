@@ -127,7 +127,9 @@ class CoreTrainer:
             p.data = self.flat[off:off + k].view_as(p)
             self.g[n] = self.grad[off:off + k].view_as(p)
             off += k
-        self.lr, self.weight_decay, self.betas, self.eps, self.t = lr, weight_decay, betas, eps, 0
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)        # Adam step number, kept on the device
+        self._prep_cache, self._graphed = {}, {}
         object.__setattr__(model, '_core_trainer', self)       # one flat bucket per model: MOTMPNet.forward reuses it under autograd
 
     # ---------------------------------------------------------------- helpers
@@ -142,33 +144,41 @@ class CoreTrainer:
                 for s in slots]
 
     # ---------------------------------------------------------------- forward + backward
-    def loss_and_grads(self, data, edge_labels, tracking_weight=1.0, zero_grad=True):
+    def loss_and_grads(self, data, edge_labels, tracking_weight=1.0, zero_grad=True, prep=None):
         """Forward (models/mpn.py:349-381), loss (pl_module.py:88-105) and backward of the core network for
         one graph (or block-diagonal batch).  Gradients are ACCUMULATED into ``self.g`` (zeroed first
         unless zero_grad=False).  Returns the loss as a 1-element device tensor."""
         if zero_grad:
             self.grad.zero_()
-        lg_all, ctx = self.forward_core(data)
+        lg_all, ctx = self.forward_core(data, prep)
         # loss (slot order on both sides) and its gradient w.r.t. the logits
         labels = edge_labels.to(lg_all.device, torch.float32).reshape(-1)[ctx['sedge'].long()].contiguous()
         loss, _, g_logits = ops.weighted_bce(lg_all, labels, weight=tracking_weight, want_grad=True)
         self.backward_core(ctx, g_logits)
         return loss
 
-    def forward_core(self, data):
+    def prepare(self, data):
+        """Index bookkeeping of one graph (slot layout, column-sorted permutation): built once per sample -- the host
+        synchronisations of the step live here, the step itself has none."""
+        n = int(data.x.shape[0])
+        lay = ops.edge_layout(data.edge_index, n)
+        e = lay.num_edges
+        srow, scol, sedge = lay.slot_row[:e], lay.slot_col[:e], lay.slot_edge[:e]
+        order = torch.argsort(scol, stable=True)                         # slots grouped by column
+        perm_c = order.to(torch.int32)
+        ptr_c = torch.zeros(n + 1, dtype=torch.int32, device=scol.device)
+        ptr_c[1:] = torch.cumsum(torch.bincount(scol.long(), minlength=n), 0).to(torch.int32)
+        return dict(lay=lay, n=n, e=e, srow=srow, scol=scol, sedge=sedge, perm_c=perm_c, ptr_c=ptr_c)
+
+    def forward_core(self, data, prep=None):
         """Forward with stored activations.  Returns (logits [num_class_steps, E] in SLOT order, ctx); ``ctx['sedge']``
         maps a slot to the caller's edge id."""
         m = self.model
         x = data.x
         pooled = ops.avgpool(x) if x.dim() > 2 else x.contiguous()
-        n = pooled.shape[0]
-        lay = ops.edge_layout(data.edge_index, n)
-        e = lay.num_edges
-        srow, scol, sedge = lay.slot_row[:e], lay.slot_col[:e], lay.slot_edge[:e]
-        order = torch.argsort(scol, stable=True)                         # slots grouped by column (index bookkeeping)
-        perm_c = order.to(torch.int32)
-        ptr_c = torch.zeros(n + 1, dtype=torch.int32, device=pooled.device)
-        ptr_c[1:] = torch.cumsum(torch.bincount(scol.long(), minlength=n), 0).to(torch.int32)
+        prep = prep or self.prepare(data)
+        lay, n, e = prep['lay'], prep['n'], prep['e']
+        srow, scol, sedge, perm_c, ptr_c = prep['srow'], prep['scol'], prep['sedge'], prep['perm_c'], prep['ptr_c']
         dev = pooled.device
         steps, first_cls = m.num_enc_steps, max(m.num_enc_steps - m.num_class_steps + 1, 1)
         n_out = lay.num_out
@@ -307,16 +317,57 @@ class CoreTrainer:
             return dist.get_world_size(group)
         return 1
 
-    def adam_step(self, grad_scale=1.0):
-        self.t += 1
-        check(lib().mpn_adam_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.flat.numel(),
-                                  float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                                  float(self.weight_decay), int(self.t), float(grad_scale), stream_ptr()), 'adam_step')
+    @property
+    def t(self):
+        return int(self.t_dev.item())
 
-    def train_step(self, data, edge_labels, tracking_weight=1.0, group=None):
+    def adam_step(self, grad_scale=1.0):
+        check(lib().mpn_adam_step_dev(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.flat.numel(),
+                                      float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                      float(self.weight_decay), ptr(self.t_dev), float(grad_scale), stream_ptr()), 'adam_step')
+
+    def train_step(self, data, edge_labels, tracking_weight=1.0, group=None, prep=None):
         """loss.backward() + gradient all-reduce (mean over ranks) + Adam, as Lightning drives it
         (pl_module.py:137-141, scripts/train.py:76 with the 8 accumulated batches spread over 8 ranks)."""
-        loss = self.loss_and_grads(data, edge_labels, tracking_weight)
+        loss = self.loss_and_grads(data, edge_labels, tracking_weight, prep=prep)
         world = self.all_reduce_grads(group)
         self.adam_step(grad_scale=1.0 / world)
         return loss
+
+    def graphed_step(self, data, edge_labels, tracking_weight=1.0, group=None):
+        """The same training step captured ONCE as a CUDA graph for this sample (its ~900 small kernels, the NCCL
+        all-reduce of the gradient bucket and Adam are then one graph launch) and replayed on every call with the same
+        ``data`` object.  Parameters, Adam state and the step counter live in fixed device buffers, so replays continue
+        the optimisation exactly like ``train_step``; ``data.x`` / ``edge_attr`` / ``edge_labels`` are read from their
+        current storage at replay time (update them in place to feed new values on the same graph structure)."""
+        key = id(data)
+        gs = self._graphed.get(key)
+        if gs is None:
+            gs = self._graphed[key] = _GraphedStep(self, data, edge_labels, tracking_weight, group)
+        return gs.replay()
+
+
+class _GraphedStep(object):
+    def __init__(self, trainer, data, edge_labels, tracking_weight, group):
+        tr = self.trainer = trainer
+        self.data, self.labels = data, edge_labels.to(data.edge_index.device, torch.float32).contiguous()
+        self.prep = tr.prepare(data)
+        state = [t.clone() for t in (tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                   # warm-up off the capture (allocator, NCCL, lazy inits)
+            for _ in range(2):
+                tr.train_step(data, self.labels, tracking_weight, group, prep=self.prep)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for dst, src in zip((tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev), state):   # the warm-up steps do not count
+            dst.copy_(src)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = tr.train_step(data, self.labels, tracking_weight, group, prep=self.prep)
+        for dst, src in zip((tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev), state):   # capture does not execute, but be explicit
+            dst.copy_(src)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

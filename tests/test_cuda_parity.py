@@ -1001,3 +1001,30 @@ def test_rounding_and_identities_match_the_reference(tag):
     ref_n, ref_l = connected_components(csr_matrix((np.ones(int(m.sum()), dtype=int), tuple(ei.cpu().numpy()[:, m])), shape=(n, n)),
                                         directed=False, return_labels=True)
     assert ncomp == ref_n and np.array_equal(lab2.cpu().numpy(), ref_l)
+
+
+def test_graphed_training_step_continues_like_the_eager_one():
+    """CoreTrainer.graphed_step (the whole step as one CUDA-graph replay, Adam step counter on the device) produces
+    the same parameters as the eager train_step after the same number of steps."""
+    from mpntrackseg_b200.training import CoreTrainer
+    c = load_case('tiny_nonrecip')
+    win, gold = c['win'], c['gold']
+    data = Data()
+    data.x = win.x.to(dev())
+    data.edge_index = torch.from_numpy(gold['edge_index'].astype(np.int64)).to(dev())
+    data.edge_attr = torch.from_numpy(gold['edge_attr']).to(dev())
+    labels = (win.ident[gold['edge_index'][0]] == win.ident[gold['edge_index'][1]]).float().to(dev())
+    trainers = []
+    for _ in range(2):
+        model = make_model(c['mp'], c['P'])
+        model.train()
+        trainers.append(CoreTrainer(model))
+    losses = [[], []]
+    for _ in range(4):
+        losses[0].append(float(trainers[0].train_step(data, labels)))
+        losses[1].append(float(trainers[1].graphed_step(data, labels)))
+    torch.cuda.synchronize()
+    assert trainers[0].t == trainers[1].t == 4
+    np.testing.assert_allclose(losses[1], losses[0], rtol=1e-6)
+    assert losses[0][-1] < losses[0][0]
+    assert torch.equal(trainers[0].flat, trainers[1].flat)
