@@ -238,6 +238,14 @@ int mpn_mp_forward(const mpn_core_weights* h_w, const mpn_edge_layout* h_g,
 int mpn_attn_aggregate(const float* z, int64_t num_nodes, int64_t feat, const mpn_edge_layout* h_g,
                        const float* logits, float* flow_in, float* flow_out, void* stream);
 
+/* Backward of mpn_attn_aggregate (training of the mask branch, pl_module/pl_module.py:107-118 back-propagates the
+ * segmentation loss through models/mpn.py:117-137): g_in / g_out [N, feat] = d loss / d flow_in, flow_out;
+ * perm_c [E] = the slots sorted by column (stable), ptr_c [N+1] its row pointer; w_slot [E] scratch.
+ * Outputs: d_z [N, feat] and d_logits [E] (caller's edge order).  Fixed-order reductions. */
+int mpn_attn_aggregate_backward(const float* z, int64_t num_nodes, int64_t feat, const mpn_edge_layout* h_g,
+                                const float* logits, const float* g_in, const float* g_out, const int32_t* perm_c,
+                                const int32_t* ptr_c, float* w_slot, float* d_z, float* d_logits, void* stream);
+
 /* pl_module/pl_module.py:88-105  _compute_loss, tracking term: pos_weight = (#edges - #pos) / #pos (0 if no
  * positive), loss = weight * sum over the classified steps of mean BCEWithLogits(logits[s], labels, pos_weight).
  * logits [steps, E], labels [E] (0/1 floats).  Outputs: loss[1], pos_weight[1] (may be NULL) and, if grad is

@@ -76,6 +76,7 @@ SIGNATURES = {
     'mpn_weighted_bce_workspace': (c_i64, []),
     'mpn_weighted_bce': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_attn_aggregate': (C.c_int, [c_vp, c_i64, c_i64, C.POINTER(EdgeLayout), c_vp, c_vp, c_vp, c_vp]),
+    'mpn_attn_aggregate_backward': (C.c_int, [c_vp, c_i64, c_i64, C.POINTER(EdgeLayout), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mpn_mp_tc_workspace': (c_i64, [c_i64, c_i64]),
     'mpn_rounding_workspace': (c_i64, [c_i64]),
     'mpn_constr_satisfaction': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64p, c_vp]),

@@ -4,8 +4,9 @@
 // One 128-node tile per group of 4 warps (thread = node row = TMEM lane), two groups per CTA.  The
 // K = 2048 contraction is streamed in chunks of 64: each thread loads its row's 64 fp32 values,
 // splits them into fp16 hi/lo (22 significant bits, same scheme as mp_step_tc.cu) and writes them to
-// a double-buffered TMEM A operand; the matching 32 KB slice of the packed fp16 hi/lo weight image is
-// staged into shared memory with cp.async; 12 MMAs (128 x 128 x 16, hi*hi + hi*lo + lo*hi) per chunk
+// a double-buffered TMEM A operand; the matching 32 KB slice of the packed fp16 hi/lo weight image (the K stream of
+// the B operand) is brought into shared memory by ONE TMA bulk copy per chunk (cp.async.bulk, completion counted in
+// bytes on an mbarrier); 12 MMAs (128 x 128 x 16, hi*hi + hi*lo + lo*hi) per chunk
 // accumulate in TMEM while the next chunk is being loaded.  The 128 -> 32 layer reuses the accumulator
 // in place as its operand.
 #include "common.cuh"
@@ -31,8 +32,8 @@ constexpr int C_D2 = 0;           // layer-2 accumulator (32 cols) over the dead
 
 constexpr int SM_W = 0;                                               // [2 groups][2 bufs][CHUNK_BYTES]
 constexpr int SM_TAIL = SM_W + 4 * CHUNK_BYTES;
-constexpr int SM_BAR = (SM_TAIL + TAIL_BYTES + 127) / 128 * 128;      // u64 bars[2 groups][2]
-constexpr int SM_TMEM = SM_BAR + 4 * 8;
+constexpr int SM_BAR = (SM_TAIL + TAIL_BYTES + 127) / 128 * 128;      // u64 bars[2 groups][2] (MMA done), wbars[2 groups][2] (weights landed)
+constexpr int SM_TMEM = SM_BAR + 8 * 8;
 constexpr int SMEM_BYTES = SM_TMEM + 16;
 
 __device__ __forceinline__ int slab_off(int n, int k16) {
@@ -74,13 +75,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_encoder_tc_kernel(const floa
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, gt = tid & (TS - 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR) + 2 * g;   // [0]/[1]: even / odd chunks
+  uint64_t* wbars = reinterpret_cast<uint64_t*>(smem + SM_BAR) + 4 + 2 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
   const int nchunks = (int)(k0 / KC);
   const uint8_t* tail_g = img + (int64_t)nchunks * CHUNK_BYTES;
   for (int i = tid; i < TAIL_BYTES / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(smem + SM_TAIL)[i] = __ldg(reinterpret_cast<const uint4*>(tail_g) + i);
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + SM_BAR) + i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + SM_BAR) + i, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_encoder_tc_kernel(const floa
   const uint32_t wbuf = smem_u32(smem + SM_W + g * 2 * CHUNK_BYTES);
   const uint64_t dbase = smem_desc_kmajor(0, 128, 256);
   __half2 vmax = __floats2half2_rn(0.f, 0.f);
-  uint32_t par[2] = {0, 0};
+  uint32_t par[2] = {0, 0}, wpar[2] = {0, 0};
 
   const int64_t tiles = (n + TS - 1) / TS;
   for (int64_t t = (int64_t)blockIdx.x * 2 + g; t < tiles; t += (int64_t)gridDim.x * 2) {
@@ -102,11 +104,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_encoder_tc_kernel(const floa
     const bool valid = row < n;
     if (!valid) row = n - 1;
     const float4* xr = reinterpret_cast<const float4*>(x + row * k0);
-    auto load_w = [&](int c) {                                       // 32 KB: 128 threads x 16 x 16 B
-      const uint8_t* src = img + (int64_t)c * CHUNK_BYTES;
-      const uint32_t dst = wbuf + (c & 1) * CHUNK_BYTES;
-#pragma unroll
-      for (int j = 0; j < CHUNK_BYTES / 16 / TS; ++j) cp_async16(dst + (j * TS + gt) * 16, src + (j * TS + gt) * 16);
+    auto load_w = [&](int c) {                                       // 32 KB weight chunk: one TMA bulk copy
+      if (gt == 0) {
+        mbar_arrive_expect_tx(&wbars[c & 1], CHUNK_BYTES);
+        tma_bulk_g2s(wbuf + (c & 1) * CHUNK_BYTES, img + (int64_t)c * CHUNK_BYTES, CHUNK_BYTES, &wbars[c & 1]);
+      }
     };
     float4 xv[KC / 4];
     load_w(0);
@@ -129,8 +131,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_encoder_tc_kernel(const floa
         tmem_st8(abuf + 8 * q, hi);
         tmem_st8(abuf + 32 + 8 * q, lo);
       }
-      cp_async_wait_all();                                           // this chunk's weights have landed
-      fence_async_smem();
+      mbar_wait(&wbars[c & 1], wpar[c & 1]); wpar[c & 1] ^= 1;       // this chunk's weights have landed
       tc_wait_st();
       tc_fence_before();
       named_barrier(1 + g, TS);

@@ -6,6 +6,7 @@
 //   3. keep (i<j) iff in_k(i,j) AND/OR in_k(j,i); pairs are emitted sorted by (i, j) (utils/graph.py:73-85),
 // with a single host synchronisation (the pair count).  Node ids are batch-global.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(SEL_THREADS) row_select_kernel(
     const float* __restrict__ dense, const int64_t* __restrict__ gptr, int64_t num_graphs, const int64_t* __restrict__ doff,
     const int64_t* __restrict__ moff, int64_t k, const int32_t* __restrict__ row_mask, uint32_t* __restrict__ thr_key,
     int32_t* __restrict__ thr_idx, uint32_t* __restrict__ M, const float* __restrict__ norm2,
-    const float* __restrict__ win_nmax, float beta, int32_t* __restrict__ amb, int32_t* __restrict__ amb_count) {
+    const float* __restrict__ win_nmax, float beta, int32_t* __restrict__ amb, int32_t* __restrict__ amb_count,
+    int64_t scratch_ld, int64_t scratch_rows) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining, s_count;
@@ -251,7 +253,9 @@ __global__ void __launch_bounds__(SEL_THREADS) row_select_kernel(
   int64_t lo = 0, hi = num_graphs;
   while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (gptr[mid] <= i) lo = mid; else hi = mid; }
   const int64_t n0 = gptr[lo], n = gptr[lo + 1] - n0, li = i - n0;
-  const float* rowp = dense + doff[lo] + li * n;
+  // scratch_ld > 0: `dense` holds exact rows of the flagged nodes only, row_mask[i] - 1 is the row's slot
+  if (scratch_ld > 0 && row_mask[i] > scratch_rows) return;
+  const float* rowp = scratch_ld > 0 ? dense + (int64_t)(row_mask[i] - 1) * scratch_ld : dense + doff[lo] + li * n;
   const int words = (int)((n + 31) >> 5);
   uint32_t* mrow = M + moff[lo] + li * words;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -365,11 +369,11 @@ template <bool kAmb>
 static void launch_row_select(int64_t max_n, int64_t n, cudaStream_t s, const float* dense, const int64_t* gptr, int64_t num_graphs,
                               const int64_t* doff, const int64_t* moff, int64_t k, const int32_t* row_mask, uint32_t* thr_key,
                               int32_t* thr_idx, uint32_t* M, const float* norm2, const float* win_nmax, float beta, int32_t* amb,
-                              int32_t* amb_count) {
+                              int32_t* amb_count, int64_t scratch_ld = 0, int64_t scratch_rows = 0) {
   const unsigned g = (unsigned)n;
 #define MPN_SEL(PER)                                                                                                     \
   row_select_kernel<kAmb, PER><<<g, SEL_THREADS, 0, s>>>(dense, gptr, num_graphs, doff, moff, k, row_mask, thr_key, thr_idx, M, \
-                                                         norm2, win_nmax, beta, amb, amb_count)
+                                                         norm2, win_nmax, beta, amb, amb_count, scratch_ld, scratch_rows)
   if (max_n <= 5 * SEL_THREADS) MPN_SEL(5);
   else if (max_n <= 9 * SEL_THREADS) MPN_SEL(9);
   else if (max_n <= 12 * SEL_THREADS) MPN_SEL(12);
@@ -459,7 +463,7 @@ __global__ void mask_pairs_kernel(const uint32_t* __restrict__ M, const uint32_t
           const int64_t lj = (int64_t)c * 32 + b;
           out_row[pos] = i;
           out_col[pos] = n0 + lj;
-          out_dist[pos] = dense[doff[lo] + li * n + lj];
+          out_dist[pos] = dense != nullptr ? dense[doff[lo] + li * n + lj] : 0.f;   // (recomputed exactly by the caller)
           ++pos;
         }
       }
@@ -499,7 +503,18 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
 int gram_fix_ambiguous(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, int64_t num_graphs,
                        int64_t num_nodes, const int64_t* doff, int64_t max_dist, float* dense, const float* norm2,
                        const uint32_t* thr_key, const int32_t* thr_idx, float beta, int32_t* amb, int32_t* amb_count,
-                       int detect, cudaStream_t s);
+                       int detect, int64_t scratch_ld, int64_t scratch_rows, cudaStream_t s);
+bool gram_thresholded_applies(const int64_t* h_gptr, int64_t num_graphs, int64_t top_k);
+int gram_thresholded_select(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,
+                            int64_t num_graphs, const int64_t* moff, int64_t max_dist, int64_t top_k, void* ws,
+                            const float* win_nmax_buf, float beta, uint32_t* M, int32_t* status, float** norm2_out,
+                            int32_t** amb_out, int32_t** amb_count_out,
+                            void (*window_max)(const float*, const int64_t*, int64_t, float*, cudaStream_t), cudaStream_t s);
+
+static void launch_window_max(const float* v, const int64_t* gptr, int64_t num_graphs, float* out, cudaStream_t s) {
+  window_max_kernel<<<(unsigned)num_graphs, 256, 0, s>>>(v, gptr, out);
+  count_launch();
+}
 
 }  // namespace mpn
 
@@ -558,7 +573,24 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   MPN_CUDA(cudaMemsetAsync(status, 0, 16, s));
 
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff, moff); count_launch();
-  if (tc) {
+  // large windows on the tensor-core path: thresholded candidate lists instead of dense N^2 blocks (MPN_KNN_DENSE=1: old path)
+  static const bool force_dense = getenv("MPN_KNN_DENSE") != nullptr;
+  const bool tg = tc && max_n <= SEL_MAX_N && !force_dense && gram_thresholded_applies(h_gptr, num_graphs, top_k);
+  int64_t scratch_rows = 0;
+  if (tg) {
+    rc = gram_thresholded_select(reid, dim, frame, gptr, h_gptr, num_graphs, moff, max_frame_dist, top_k,
+                                 static_cast<char*>(ws) + cv.off, win_nmax, 2e-6f, M, status, &norm2, &amb, &amb_count,
+                                 launch_window_max, s);
+    if (rc) return rc;
+    // flagged rows (uncertain top-k set, list overflow, too few candidates): exact fp32 row into a scratch slot of the
+    // (otherwise unused) dense area, ranked by the dense row select
+    scratch_rows = sum_sq / max_n;
+    rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f, amb,
+                            amb_count, 0, max_n, scratch_rows, s);
+    if (rc) return rc;
+    launch_row_select<false>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, amb, tk, ti, M, nullptr, nullptr, 0.f,
+                             nullptr, nullptr, max_n, scratch_rows);
+  } else if (tc) {
     rc = gram_dist_blocks(reid, dim, frame, gptr, h_gptr, num_graphs, doff, max_frame_dist,
                           static_cast<char*>(ws) + cv.off, dense, status, &norm2, &amb, &amb_count,
                           max_n <= SEL_MAX_N ? 1 : 0, s);
@@ -572,13 +604,15 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   // windows of up to SEL_MAX_N nodes: fused row select -> bit matrices -> pairs; larger windows: the general kernels
   const bool fused = prune && max_n <= SEL_MAX_N;
   if (fused) {
-    if (tc) {
+    if (tg) {
+      // bit matrix rows are already in place
+    } else if (tc) {
       window_max_kernel<<<(unsigned)num_graphs, 256, 0, s>>>(norm2, gptr, win_nmax); count_launch();
       launch_row_select<true>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, nullptr, tk, ti, M, norm2, win_nmax, 2e-6f,
                               amb, amb_count);
       // rows whose top-k set is not certain: exact fp32 distances, ranked again
       rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
-                              amb, amb_count, 0, s);
+                              amb, amb_count, 0, 0, 0, s);
       if (rc) return rc;
       launch_row_select<false>(max_n, n, s, dense, gptr, num_graphs, doff, moff, top_k, amb, tk, ti, M, nullptr, nullptr, 0.f,
                                nullptr, nullptr);
@@ -589,14 +623,14 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
     const int64_t max_words = (max_n + 31) >> 5;
     const unsigned tgrid = (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(max_words * max_words * 32, 256), 1), 4096);
     bit_transpose_kernel<<<dim3(tgrid, (unsigned)num_graphs), 256, 0, s>>>(M, MT, gptr, moff); count_launch();
-    mask_pairs_kernel<false><<<wgrid, 256, 0, s>>>(M, MT, dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
+    mask_pairs_kernel<false><<<wgrid, 256, 0, s>>>(M, MT, tg ? nullptr : dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
                                                   row_start, nullptr, nullptr, nullptr); count_launch();
   } else {
     if (prune) {
       batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, nullptr, tk, ti); count_launch();
       if (tc) {                                                       // repair rows whose top-k set is not certain
         rc = gram_fix_ambiguous(reid, dim, frame, gptr, num_graphs, n, doff, max_frame_dist, dense, norm2, tk, ti, 2e-6f,
-                                amb, amb_count, 1, s);
+                                amb, amb_count, 1, 0, 0, s);
         if (rc) return rc;
         batch_row_kth_kernel<<<(unsigned)n, 256, 0, s>>>(dense, gptr, num_graphs, doff, top_k, amb, tk, ti); count_launch();
       }
@@ -614,6 +648,7 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
   MPN_CUDA(cudaMemcpyAsync(&h_flags[0], status, 4, cudaMemcpyDeviceToHost, s));
   if (tc) MPN_CUDA(cudaMemcpyAsync(&h_flags[1], amb_count, 4, cudaMemcpyDeviceToHost, s));
   MPN_CUDA(cudaStreamSynchronize(s));
+  if (tg && h_flags[1] > scratch_rows) h_flags[0] = 1;              // more flagged rows than scratch slots: exact kernel
   if (tc && h_flags[0] != 0)                                        // embeddings beyond the fp16 range: exact kernel
     return mpn_knn_graph_pairs(frame, gptr, h_gptr, num_graphs, reid, dim, top_k, reciprocal, max_frame_dist, 0, ws,
                                capacity, out_row, out_col, out_dist, graph_pair_ptr, h_graph_pair_ptr, h_stats, stream);
@@ -624,7 +659,7 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
     return MPN_ENOSPC;
   }
   if (fused) {
-    mask_pairs_kernel<true><<<wgrid, 256, 0, s>>>(M, MT, dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
+    mask_pairs_kernel<true><<<wgrid, 256, 0, s>>>(M, MT, tg ? nullptr : dense, gptr, num_graphs, doff, moff, frame, n, max_frame_dist, reciprocal,
                                                  row_start, out_row, out_col, out_dist); count_launch();
   } else {
     knn_pairs_kernel<true><<<wgrid, 256, 0, s>>>(dense, gptr, num_graphs, doff, frame, n, max_frame_dist, tk, ti, prune,

@@ -191,10 +191,10 @@ class TimeAwareAttentionModel(nn.Module):
         super().__init__()
         self.node_model = node_model        # the two attention MLPs are built and dropped by the reference (:106-109)
 
-    def aggregate(self, x, layout, logits, differentiable=False):
-        if differentiable:
+    def aggregate(self, x, layout, logits, train_ctx=None):
+        if train_ctx is not None:
             from ..training import AttnAggregate
-            flow_in, flow_out = AttnAggregate.apply(x, logits, layout)
+            flow_in, flow_out = AttnAggregate.apply(x, logits, layout, train_ctx['perm_c'], train_ctx['ptr_c'])
         else:
             flow_in, flow_out = ops.attn_aggregate(x, layout, logits)
         return self.node_model(torch.cat((x, flow_in, flow_out), dim=1))
@@ -402,10 +402,12 @@ class MOTMPNet(nn.Module):
             if return_state:
                 raise NotImplementedError('return_state is an inference-only option')
             tr = self.core_trainer()
-            logits = tr.autograd_logits(data)
-            out = {'classified_edges': [logits[i].view(-1, 1) for i in range(logits.shape[0])], 'mask_predictions': []}
+            first_class_step = max(self.num_enc_steps - self.num_class_steps + 1, 1)
+            logits = tr.autograd_logits(data, all_steps=x_ext is not None)
+            skip = first_class_step - 1 if x_ext is not None else 0
+            out = {'classified_edges': [logits[i].view(-1, 1) for i in range(skip, logits.shape[0])], 'mask_predictions': []}
             if x_ext is not None:
-                out['mask_predictions'] = self._mask_branch_train(x_ext, data, tr)
+                out['mask_predictions'] = self._mask_branch_train(x_ext, logits, tr, first_class_step)
             return out
         layout = ops.edge_layout(edge_index, x.shape[0])
         first_class_step = self.num_enc_steps - self.num_class_steps + 1
@@ -432,12 +434,13 @@ class MOTMPNet(nn.Module):
             tr = CoreTrainer(self)
         return tr
 
-    def _mask_branch_train(self, x_ext, data, tr):
-        """Mask predictions in training mode (pl_module.py:107-118 trains them with a BCE on the valid ids).
-        The convolution stacks are torch modules, so autograd reaches every mask-branch parameter; the attention
-        weights come from the DETACHED per-step logits of the core network (the mask loss does not back-propagate
-        into the tracking network here; the reference lets it)."""
-        raise NotImplementedError('training through the attention / mask branch is not built yet')
+    def _mask_branch_train(self, x_ext, logits, tr, first_class_step):
+        """Mask predictions in training mode (pl_module.py:107-118 adds their BCE on the matched detections to the
+        loss).  The convolution stacks are torch modules; the attentive aggregation is ``training.AttnAggregate`` with
+        hand-written backward kernels, so the segmentation loss reaches every mask-branch parameter and, through the
+        attention weights (softmax of every step's logits), the tracking network -- as in the reference."""
+        c = tr.last_ctx
+        return self._mask_branch(x_ext, c['lay'], logits, first_class_step, train_ctx=c)
 
     def _core(self, xs, edge_attr, layout, first_needed, want_state=False, encoded=False):
         """Encoders + step loop.  The tensor-core kernels report fp16-range overflow through one status
@@ -466,14 +469,14 @@ class MOTMPNet(nn.Module):
         del keep
         return res
 
-    def _mask_branch(self, x_ext, layout, logits, first_class_step, differentiable=False):
+    def _mask_branch(self, x_ext, layout, logits, first_class_step, train_ctx=None):
         """Attentive node-feature-map updates + mask head per classified step.
         reference: models/mpn.py:356,360,369-385 (and :387-392 for num_enc_steps == 0)"""
         z0 = self.node_ext_encoder(x_ext)
         z, masks = z0, []
         for step in range(1, self.num_enc_steps + 1):
             zc = torch.cat((z0, z), dim=1).contiguous()                # reattach the initial encoding (:373)
-            z = self.MPAttentionNet.aggregate(zc, layout, logits[step - 1], differentiable=differentiable)
+            z = self.MPAttentionNet.aggregate(zc, layout, logits[step - 1], train_ctx=train_ctx)
             if step >= first_class_step:
                 masks.append(self.mask_predictor(x_ext, z))
         if self.num_enc_steps == 0:

@@ -411,6 +411,24 @@ def attn_aggregate(z, layout, logits):
     return fin, fout
 
 
+def attn_aggregate_backward(z, layout, logits, g_in, g_out, perm_c, ptr_c):
+    """(d_z like z, d_logits [E] in the caller's edge order) of ``attn_aggregate`` for the output gradients
+    g_in / g_out; perm_c / ptr_c: the slots sorted by column and their row pointer (int32)."""
+    z = _req(z, torch.float32, 'z')
+    lg = _req(logits.reshape(-1), torch.float32, 'logits')
+    gi, go = _req(g_in, torch.float32, 'g_in'), _req(g_out, torch.float32, 'g_out')
+    pc, qc = _req(perm_c, torch.int32, 'perm_c'), _req(ptr_c, torch.int32, 'ptr_c')
+    n = z.shape[0]
+    feat = z[0].numel() if n else 0
+    dz = torch.empty_like(z)
+    dl = torch.zeros_like(lg)
+    wslot = torch.empty(max(layout.num_edges, 1), dtype=torch.float32, device=z.device)
+    g = layout.c_struct()
+    check(lib().mpn_attn_aggregate_backward(ptr(z), n, feat, C.byref(g), ptr(lg), ptr(gi), ptr(go), ptr(pc), ptr(qc), ptr(wslot),
+                                            ptr(dz), ptr(dl), stream_ptr()), 'attn_aggregate_backward')
+    return dz, dl
+
+
 def weighted_bce(logits, labels, weight=1.0, want_grad=False):
     """Tracking loss over the classified steps: (loss scalar tensor, pos_weight tensor[, d loss / d logits]).
     logits: [S, E] tensor or the list ``outputs['classified_edges']``.  pl_module/pl_module.py:88-105"""

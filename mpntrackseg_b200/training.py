@@ -82,12 +82,14 @@ CORE_PREFIXES = ('encoder.', 'classifier.', 'MPNet.')
 
 
 class _CoreLogits(torch.autograd.Function):
-    """forward_core / backward_core as one autograd node over the core parameters."""
+    """forward_core / backward_core as one autograd node over the core parameters.  With ``all_steps`` the output holds
+    the logits of EVERY message-passing step (the attention branch reads them all, models/mpn.py:377)."""
 
     @staticmethod
-    def forward(ctx, trainer, data, *params):
-        lg_slot, c = trainer.forward_core(data)
+    def forward(ctx, trainer, data, all_steps, *params):
+        lg_slot, c = trainer.forward_core(data, all_steps=all_steps)
         ctx.trainer, ctx.c = trainer, c
+        trainer.last_ctx = c
         out = torch.empty_like(lg_slot)
         out[:, c['sedge'].long()] = lg_slot                            # slot order -> the caller's edge order
         return out
@@ -97,7 +99,26 @@ class _CoreLogits(torch.autograd.Function):
         tr, c = ctx.trainer, ctx.c
         tr.grad.zero_()
         tr.backward_core(c, g_out[:, c['sedge'].long()].contiguous())
-        return (None, None) + tuple(g.clone() for g in tr.g.values())
+        return (None, None, None) + tuple(g.clone() for g in tr.g.values())
+
+
+class AttnAggregate(torch.autograd.Function):
+    """``ops.attn_aggregate`` with its hand-written backward (d z and d logits), so that the segmentation loss reaches
+    the node feature maps AND, through the attention weights, the tracking network (models/mpn.py:117-137)."""
+
+    @staticmethod
+    def forward(ctx, z, logits, layout, perm_c, ptr_c):
+        z = z.contiguous()
+        flow_in, flow_out = ops.attn_aggregate(z, layout, logits)
+        ctx.save_for_backward(z, logits, perm_c, ptr_c)
+        ctx.layout = layout
+        return flow_in, flow_out
+
+    @staticmethod
+    def backward(ctx, g_in, g_out):
+        z, logits, perm_c, ptr_c = ctx.saved_tensors
+        dz, dl = ops.attn_aggregate_backward(z, ctx.layout, logits, g_in.contiguous(), g_out.contiguous(), perm_c, ptr_c)
+        return dz, dl.view_as(logits), None, None, None
 
 
 class CoreTrainer:
@@ -170,7 +191,7 @@ class CoreTrainer:
         ptr_c[1:] = torch.cumsum(torch.bincount(scol.long(), minlength=n), 0).to(torch.int32)
         return dict(lay=lay, n=n, e=e, srow=srow, scol=scol, sedge=sedge, perm_c=perm_c, ptr_c=ptr_c)
 
-    def forward_core(self, data, prep=None):
+    def forward_core(self, data, prep=None, all_steps=False):
         """Forward with stored activations.  Returns (logits [num_class_steps, E] in SLOT order, ctx); ``ctx['sedge']``
         maps a slot to the caller's edge id."""
         m = self.model
@@ -205,7 +226,7 @@ class CoreTrainer:
         e0 = acts_e[-1]
 
         # ---- message-passing steps
-        xs, es, saved, logits = x0, e0, [], []
+        xs, es, saved, logits, logit_steps = x0, e0, [], [], []
         ranges = (('out', 0, n_out, dn), ('in', n_out, e, 0))            # (name, slot range, column offset in [flow_in|flow_out])
         for step in range(1, steps + 1):
             a = torch.empty((e, 4 * dn + 2 * de), dtype=torch.float32, device=dev)
@@ -228,14 +249,16 @@ class CoreTrainer:
                 segment_sum(msg, 0, dn, lay.out_ptr if name == 'out' else lay.in_ptr, None, f, coff)
             xs_new = node_lin.fwd(f)
             saved.append((a, h, e2, c1, b, g_, msg, f, xs_new))
-            if step >= first_cls:
+            if all_steps or step >= first_cls:
                 logits.append(lg.view(-1))
+                logit_steps.append(step)
             xs, es = xs_new, e2
         if steps == 0:
             raise NotImplementedError('training with num_enc_steps == 0')
 
         ctx = dict(lay=lay, sedge=sedge, srow=srow, scol=scol, perm_c=perm_c, ptr_c=ptr_c, n=n, e=e, n_out=n_out,
-                   steps=steps, first_cls=first_cls, saved=saved, acts_n=acts_n, acts_e=acts_e, dn=dn, de=de)
+                   steps=steps, first_cls=first_cls, saved=saved, acts_n=acts_n, acts_e=acts_e, dn=dn, de=de,
+                   logit_steps=logit_steps)
         return torch.stack(logits), ctx
 
     def backward_core(self, ctx, g_logits):
@@ -252,6 +275,7 @@ class CoreTrainer:
         cls = self._mlp('classifier.edge_model')
         ranges = (('out', 0, n_out, dn), ('in', n_out, e, 0))
         g_logits = g_logits.contiguous()
+        row_of = {step: i for i, step in enumerate(ctx['logit_steps'])}   # row of g_logits that belongs to a step
 
         # ---- backward through the steps
         gxs = torch.zeros((n, dn), dtype=torch.float32, device=dev)
@@ -273,8 +297,8 @@ class CoreTrainer:
                 colsum(gg, mask=g_[s0:s1], out=l0.gb, accumulate=True)
                 gemm(gg, l0.w, mask=g_[s0:s1], out=gb[s0:s1])
             ge2 = ge2_next + gb[:, 2 * dn:]                                             # e' feeds the flow MLPs and step+1
-            if step >= first_cls:
-                gl = g_logits[step - first_cls].view(-1, 1)
+            if step in row_of:
+                gl = g_logits[row_of[step]].view(-1, 1)
                 gc1 = cls[1].bwd(c1, None, gl)
                 gemm(gc1, e2, ta=True, mask=c1, out=cls[0].gw, accumulate=True)
                 colsum(gc1, mask=c1, out=cls[0].gb, accumulate=True)
@@ -303,10 +327,11 @@ class CoreTrainer:
             g_act = enc_e[i].bwd(acts_e[i], acts_e[i + 1], g_act, need_gx=i > 0)
 
     # ---------------------------------------------------------------- autograd bridge
-    def autograd_logits(self, data):
-        """Logits [num_class_steps, E] in the CALLER'S edge order, attached to the autograd graph of the core
-        parameters: ``loss.backward()`` (pl_module.py:126-135) runs ``backward_core`` and fills ``p.grad``."""
-        return _CoreLogits.apply(self, data, *self.named.values())
+    def autograd_logits(self, data, all_steps=False):
+        """Logits [num_class_steps, E] (or [num_enc_steps, E] with ``all_steps``) in the CALLER'S edge order, attached to
+        the autograd graph of the core parameters: ``loss.backward()`` (pl_module.py:126-135) runs ``backward_core`` and
+        fills ``p.grad``."""
+        return _CoreLogits.apply(self, data, all_steps, *self.named.values())
 
     # ---------------------------------------------------------------- optimizer
     def all_reduce_grads(self, group=None):

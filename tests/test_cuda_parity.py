@@ -835,9 +835,57 @@ def test_motmpnet_forward_under_autograd_fills_parameter_gradients():
     with torch.no_grad():
         moved = model.eval()(data)['classified_edges'][-1]
     assert float((moved - ref_logits[-1]).abs().max()) > 0        # the kernels read the updated weights
-    data.x_ext = torch.zeros(win.N, 256, 14, 14, device=dev())
-    with pytest.raises(NotImplementedError):
-        model.train()(data)
+
+
+def test_training_through_the_mask_branch_matches_autograd_of_the_oracle():
+    """The reference's full training loss (pl_module.py:88-120: weighted tracking BCE + segmentation BCE on the matched
+    detections, every classified step) on the full model: model.train()(data) with x_ext, torch loss, loss.backward().
+    Gradients of ALL parameters (mask branch through cuDNN + the attention backward kernels, tracking network through the
+    attention weights and the logits) against autograd through the oracle."""
+    import torch.nn.functional as F
+    c = load_case('tiny_full')
+    win, gold, mp, P = c['win'], c['gold'], c['mp'], c['P']
+    ei = torch.from_numpy(gold['edge_index'].astype(np.int64))
+    ea = torch.from_numpy(gold['edge_attr'])
+    labels = (win.ident[ei[0]] == win.ident[ei[1]]).float()
+    g = torch.Generator().manual_seed(17)
+    gt_masks = (torch.rand(win.N, 1, 56, 56, generator=g) > 0.5).float()
+    ixs = torch.arange(0, win.N, 3)
+    w_track, w_seg = 0.8, 0.6
+
+    def full_loss(out, lab, gtm):
+        pos = lab.sum()
+        pw = (lab.shape[0] - pos) / pos
+        loss = 0
+        for lg, mk in zip(out['classified_edges'], out['mask_predictions']):
+            loss = loss + w_track * F.binary_cross_entropy_with_logits(lg.view(-1), lab, pos_weight=pw)
+            loss = loss + w_seg * F.binary_cross_entropy_with_logits(mk[ixs.to(mk.device)], gtm[ixs.to(gtm.device)])
+        return loss
+
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ref_out = mpn_ref.mpn_forward(Pg, mp, win.x, ei, ea, x_ext=win.x_ext)
+    assert tuple(ref_out['mask_predictions'][-1].shape) == tuple(gt_masks.shape)
+    ref_loss = full_loss(ref_out, labels, gt_masks)
+    ref_loss.backward()
+    model = make_model(mp, P, 'fp32').train()
+    data = Data()
+    data.x, data.edge_index, data.edge_attr, data.x_ext = win.x.to(dev()), ei.to(dev()), ea.to(dev()), win.x_ext.to(dev())
+    out = model(data)
+    assert len(out['classified_edges']) == mp['num_class_steps'] == len(out['mask_predictions'])
+    loss = full_loss(out, labels.to(dev()), gt_masks.to(dev()))
+    assert abs(float(loss) - float(ref_loss)) <= 5e-4 * max(1.0, abs(float(ref_loss)))
+    loss.backward()
+    named = dict(model.named_parameters())
+    checked = 0
+    for k, p in Pg.items():
+        if p.grad is None:
+            continue
+        got = named[k].grad
+        assert got is not None, k
+        scale = float(p.grad.abs().max()) + 1e-12
+        assert float((got.cpu() - p.grad).abs().max()) / scale <= 3e-3, k
+        checked += 1
+    assert checked >= 40 and any(k.startswith('MPAttentionNet') for k in Pg) and Pg['MPNet.node_model.node_model.0.weight'].grad is not None
 
 
 def test_adam_step_matches_torch_adam():
@@ -1028,3 +1076,79 @@ def test_graphed_training_step_continues_like_the_eager_one():
     np.testing.assert_allclose(losses[1], losses[0], rtol=1e-6)
     assert losses[0][-1] < losses[0][0]
     assert torch.equal(trainers[0].flat, trainers[1].flat)
+
+
+# ------------------------------------------------------------------ property tests (hypothesis)
+def _hyp():
+    hyp = pytest.importorskip('hypothesis')
+    return hyp, hyp.strategies
+
+
+def test_property_knn_mask_equals_oracle_on_random_windows():
+    """get_knn_mask on random small windows (random sizes, k, reciprocity, duplicated embeddings -> exact ties):
+    the CUDA mask equals the oracle's bit for bit."""
+    hyp, st = _hyp()
+    from mpntrackseg_b200.utils.graph import get_knn_mask
+
+    @hyp.settings(max_examples=25, deadline=None, derandomize=True)
+    @hyp.given(t=st.integers(2, 6), d=st.integers(1, 9), k=st.integers(1, 12), recip=st.booleans(), sym=st.booleans(),
+               dup=st.booleans(), seed=st.integers(0, 10_000))
+    def run(t, d, k, recip, sym, dup, seed):
+        g = torch.Generator().manual_seed(seed)
+        n = t * d
+        frame = torch.arange(t).repeat_interleave(d)
+        reid = torch.randn(n, 32, generator=g)
+        if dup and n > 3:
+            reid[n // 2] = reid[0]                                                   # exact ties at some k boundary
+            reid[n - 1] = reid[1]
+        pairs = graph_ref.time_valid_pairs(frame, 'max')
+        if pairs.shape[1] == 0:
+            return
+        dist = graph_ref.pair_reid_dist(reid, pairs)
+        if sym:
+            pairs, dist = torch.cat((pairs, pairs.flip(0)), dim=1), torch.cat((dist, dist))
+        ref = graph_ref.knn_keep_mask(dist, pairs, n, k, recip, symmetric_edges=sym)
+        got = get_knn_mask(dist, pairs, n, k, use_cuda=True, reciprocal_k_nns=recip, symmetric_edges=sym)
+        assert torch.equal(got.cpu(), ref)
+
+    run()
+
+
+def test_property_greedy_projection_and_components_on_random_graphs():
+    """Random prediction graphs: the projection is feasible (every flow <= 1), only switches edges off, keeps every
+    edge of a node that was feasible to begin with unless its other endpoint forced it off, is deterministic; the
+    component labels equal scipy's for any edge order."""
+    hyp, st = _hyp()
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    from mpntrackseg_b200 import ops
+
+    @hyp.settings(max_examples=25, deadline=None, derandomize=True)
+    @hyp.given(n=st.integers(2, 60), dens=st.floats(0.02, 0.6), seed=st.integers(0, 10_000))
+    def run(n, dens, seed):
+        g = torch.Generator().manual_seed(seed)
+        ii, jj = torch.triu_indices(n, n, offset=1)
+        keep = torch.rand(ii.numel(), generator=g) < dens
+        if int(keep.sum()) == 0:
+            return
+        ei = torch.stack((ii[keep], jj[keep])).to(dev())
+        preds = (torch.rand(ei.shape[1], generator=g).round(decimals=1)).to(dev())        # many exact ties
+        r1, rate = ops.greedy_project(ei, preds, n)
+        r2, _ = ops.greedy_project(ei, preds, n)
+        assert torch.equal(r1, r2)
+        assert bool(((r1 == 0) | (preds > 0.5)).all())                                   # nothing is switched on
+        _, fin, fout = ops.constr_satisfaction(ei, r1, n, undirected_edges=False)
+        assert float(fin.max()) <= 1 and float(fout.max()) <= 1
+        r0 = (preds > 0.5).float()
+        rate0, fin0, fout0 = ops.constr_satisfaction(ei, r0, n, undirected_edges=False)
+        assert rate == rate0
+        untouched = (fout0[ei[0]] <= 1) & (fin0[ei[1]] <= 1)                              # both constraints fine initially
+        assert torch.equal(r1[untouched], r0[untouched])
+        perm = torch.randperm(ei.shape[1], generator=g).to(dev())
+        labels, ncomp = ops.connected_components(ei[:, perm], r1[perm], n)
+        m = r1.cpu().numpy() == 1
+        ref_n, ref_l = connected_components(csr_matrix((np.ones(int(m.sum()), dtype=int), tuple(ei.cpu().numpy()[:, m])), shape=(n, n)),
+                                            directed=False, return_labels=True)
+        assert ncomp == ref_n and np.array_equal(labels.cpu().numpy(), ref_l)
+
+    run()
