@@ -360,38 +360,39 @@ class CoreTrainer:
         return loss
 
     def graphed_step(self, data, edge_labels, tracking_weight=1.0, group=None):
-        """The same training step captured ONCE as a CUDA graph for this sample (its ~900 small kernels, the NCCL
-        all-reduce of the gradient bucket and Adam are then one graph launch) and replayed on every call with the same
-        ``data`` object.  Parameters, Adam state and the step counter live in fixed device buffers, so replays continue
-        the optimisation exactly like ``train_step``; ``data.x`` / ``edge_attr`` / ``edge_labels`` are read from their
+        """The same training step with its compute part (forward with activations, loss, backward: ~900 small kernels)
+        captured ONCE as a CUDA graph for this sample and replayed on every call with the same ``data`` object; the NCCL
+        all-reduce of the gradient bucket and the Adam step (two kernels, step counter on the device) follow on the same
+        stream outside the graph.  Parameters and gradients live in fixed device buffers, so replays continue the
+        optimisation exactly like ``train_step``; ``data.x`` / ``edge_attr`` / ``edge_labels`` are read from their
         current storage at replay time (update them in place to feed new values on the same graph structure)."""
         key = id(data)
         gs = self._graphed.get(key)
         if gs is None:
-            gs = self._graphed[key] = _GraphedStep(self, data, edge_labels, tracking_weight, group)
-        return gs.replay()
+            gs = self._graphed[key] = _GraphedStep(self, data, edge_labels, tracking_weight)
+        loss = gs.replay()
+        world = self.all_reduce_grads(group)
+        self.adam_step(grad_scale=1.0 / world)
+        return loss
 
 
 class _GraphedStep(object):
-    def __init__(self, trainer, data, edge_labels, tracking_weight, group):
+    """CUDA graph of ``CoreTrainer.loss_and_grads`` for one sample (no collective inside the capture)."""
+
+    def __init__(self, trainer, data, edge_labels, tracking_weight):
         tr = self.trainer = trainer
         self.data, self.labels = data, edge_labels.to(data.edge_index.device, torch.float32).contiguous()
         self.prep = tr.prepare(data)
-        state = [t.clone() for t in (tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev)]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                                   # warm-up off the capture (allocator, NCCL, lazy inits)
+        with torch.cuda.stream(side):                                   # warm-up off the capture (allocator, lazy inits)
             for _ in range(2):
-                tr.train_step(data, self.labels, tracking_weight, group, prep=self.prep)
+                tr.loss_and_grads(data, self.labels, tracking_weight, prep=self.prep)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for dst, src in zip((tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev), state):   # the warm-up steps do not count
-            dst.copy_(src)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss = tr.train_step(data, self.labels, tracking_weight, group, prep=self.prep)
-        for dst, src in zip((tr.flat, tr.exp_avg, tr.exp_avg_sq, tr.t_dev), state):   # capture does not execute, but be explicit
-            dst.copy_(src)
+            self.loss = tr.loss_and_grads(data, self.labels, tracking_weight, prep=self.prep)
 
     def replay(self):
         self.graph.replay()
