@@ -40,15 +40,16 @@ void profile_mark(int kind, bool begin, cudaStream_t s) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-    cached = p.multiProcessorCount;
+  // per device: one process may drive several GPUs (the cache is keyed by the current device)
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
 }
 
 // ---------------------------------------------------------------- exclusive scan

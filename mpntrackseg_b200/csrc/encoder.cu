@@ -190,7 +190,7 @@ int mpn_linear(const float* in, int64_t m, int64_t k, const float* w, const floa
   if (m == 0) return MPN_OK;
   MPN_CHECK_ARG(in && w && out, "linear: null pointer");
   dim3 grid((unsigned)ceil_div(o, LT), (unsigned)ceil_div(m, LT));
-  MPN_CHECK_ARG(grid.y <= 65535u * 1024u, "linear: too many rows");
+  MPN_CHECK_ARG(grid.y <= 65535u, "linear: at most %d rows per call (gridDim.y limit)", 65535 * LT);
   linear_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, m, k, w, b, o, relu, out); count_launch();
   MPN_LAUNCH_CHECK();
   return MPN_OK;

@@ -252,12 +252,8 @@ int mpn_node_encoder_tc(const float* x, int64_t n, int64_t k0, const float* w0, 
   MPN_CHECK_ARG(x && w0 && b0 && w1 && b1 && out, "node_encoder_tc: null pointer");
   MPN_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0, "node_encoder_tc: x must be 16-byte aligned");
   uint8_t* img = static_cast<uint8_t*>(ws);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MPN_CUDA(cudaFuncSetAttribute(enc::node_encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  enc::SMEM_BYTES));
-    attr_set = true;
-  }
+  MPN_CUDA(cudaFuncSetAttribute(enc::node_encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                enc::SMEM_BYTES));
   enc::pack_kernel<<<64, 256, 0, s>>>(w0, b0, w1, b1, k0, img); count_launch();
   const int64_t tiles = ceil_div(n, enc::TS);
   int grid = (int)std::min<int64_t>(ceil_div(tiles, 2), sm_count());

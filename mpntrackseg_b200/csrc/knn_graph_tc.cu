@@ -361,22 +361,42 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gram_blocks2_kernel(Gram2Args a
       } else {
         // thresholded pass (upper-triangular tiles): one value per pair, offered to both rows' candidate lists.  Pairs
         // that are not time-valid are dropped by cand_select_kernel (they rarely pass the threshold).
+        // Two sweeps over the 32 columns: the first only computes and votes (no memory traffic), then every lane reserves
+        // list slots ONCE for its row and once for its column (two atomics per lane per tile, all in flight together),
+        // the second writes the few passing entries at their ranks.
         const int row_l = (int)li, colbase = tj * TS + cg * 32;
         const bool diag = ti == tj;
+        float d2v[32];
+        uint32_t rowmask = 0u, colmask = 0u;                     // bit j: column j passes for my row / lane j's column: rows that pass
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float nb = __shfl_sync(0xffffffffu, nb_l, j), sb = __shfl_sync(0xffffffffu, sb_l, j);
           const float tau_j = __shfl_sync(0xffffffffu, tau_l, j);
           const int lj = colbase + j;
-          const float d2 = fmaxf((na + nb) - 2.f * __uint_as_float(j < 16 ? acc0[j] : acc1[j - 16]) + 2.f * eps * (sa - sb) + keps, 0.f);
+          d2v[j] = fmaxf((na + nb) - 2.f * __uint_as_float(j < 16 ? acc0[j] : acc1[j - 16]) + 2.f * eps * (sa - sb) + keps, 0.f);
           const bool live = valid && lj < (int)n && (!diag || lj > row_l);
-          if (live && d2 <= tau_i) {
-            const int slot = atomicAdd(&a.cand_cnt[n0 + li], 1);
-            if (slot < CAND_CAP) a.cand[(n0 + li) * CAND_CAP + slot] = make_uint2((uint32_t)lj, __float_as_uint(d2));
+          if (live && d2v[j] <= tau_i) rowmask |= 1u << j;
+          const uint32_t vote = __ballot_sync(0xffffffffu, live && d2v[j] <= tau_j);
+          if (lane == j) colmask = vote;
+        }
+        const int rcnt = __popc(rowmask), ccnt = __popc(colmask);
+        const int64_t crow = n0 + (int64_t)colbase + lane;        // the row this lane reserves column-side slots for
+        int rbase = 0, cbase = 0;
+        if (rcnt) rbase = atomicAdd(&a.cand_cnt[n0 + li], rcnt);
+        if (ccnt) cbase = atomicAdd(&a.cand_cnt[crow], ccnt);
+        uint2* rlist = a.cand + (n0 + li) * CAND_CAP;
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if ((rowmask >> j) & 1u) {
+            const int slot = rbase + __popc(rowmask & ((1u << j) - 1u));
+            if (slot < CAND_CAP) rlist[slot] = make_uint2((uint32_t)(colbase + j), __float_as_uint(d2v[j]));
           }
-          if (live && d2 <= tau_j) {
-            const int slot = atomicAdd(&a.cand_cnt[n0 + lj], 1);
-            if (slot < CAND_CAP) a.cand[(n0 + lj) * CAND_CAP + slot] = make_uint2((uint32_t)row_l, __float_as_uint(d2));
+          const uint32_t cm = __shfl_sync(0xffffffffu, colmask, j);
+          const int cb = __shfl_sync(0xffffffffu, cbase, j);
+          if ((cm >> lane) & 1u) {
+            const int slot = cb + __popc(cm & lt);
+            if (slot < CAND_CAP) a.cand[(n0 + (int64_t)colbase + j) * CAND_CAP + slot] = make_uint2((uint32_t)row_l, __float_as_uint(d2v[j]));
           }
         }
       }

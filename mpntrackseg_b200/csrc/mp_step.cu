@@ -343,12 +343,8 @@ static int launch_step(const mpn_core_weights* w, const mpn_edge_layout* g, cons
                        cudaStream_t s) {
   using W = Shipped;
   const int64_t n = g->num_nodes, e = g->num_edges;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MPN_CUDA(cudaFuncSetAttribute(mp_edge_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)W::SMEM_BYTES));
-    attr_set = true;
-  }
+  MPN_CUDA(cudaFuncSetAttribute(mp_edge_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)W::SMEM_BYTES));
   const int tiles_out = (int)ceil_div(g->num_out, TS);
   const int tiles_in = (int)ceil_div(e - g->num_out, TS);
   const int total_tiles = tiles_out + tiles_in;

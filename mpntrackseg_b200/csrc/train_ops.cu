@@ -207,6 +207,7 @@ int mpn_gemm(const float* a, int64_t lda, int trans_a, const float* mask_a, int6
   MPN_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "gemm: negative size");
   if (m == 0 || n == 0) return MPN_OK;
   MPN_CHECK_ARG(c != nullptr && (k == 0 || (a && b)), "gemm: null pointer");
+  MPN_CHECK_ARG(ceil_div(m, GT) <= 65535, "gemm: at most %d rows per call (gridDim.y limit)", 65535 * GT);
   cudaStream_t s = as_stream(stream);
   keep_async_pool();
   const int64_t tiles = ceil_div(n, GT) * ceil_div(m, GT);
