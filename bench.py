@@ -418,7 +418,10 @@ def run_b200(a):
     with torch.no_grad():
         ref_last = step(devin)[1].logits[-1].cpu()
     e2e_max_diff = float((res - ref_last).abs().max())
-    assert e2e_max_diff == 0.0, f'store arm and device-resident arm disagree by {e2e_max_diff}'
+    # bit-identical on the tensor-core path; if the forward fell back to the fp32 kernels (state beyond the scaled fp16
+    # range) the device arm also re-encodes the nodes in fp32 while this arm keeps its tensor-core encoding: rounding level
+    assert e2e_max_diff <= 1e-5 * max(1.0, float(ref_last.abs().max())), \
+        f'store arm and device-resident arm disagree by {e2e_max_diff}'
 
     # ---- second number: raw [N,2048,8,4] maps from pinned memory every step (the round-1 e2e definition)
     raw_steps = min(a.steps, 5)
