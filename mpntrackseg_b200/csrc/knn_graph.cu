@@ -574,7 +574,7 @@ int mpn_knn_graph_pairs(const int64_t* frame, const int64_t* gptr, const int64_t
 
   graph_offsets_kernel<<<1, 32, 0, s>>>(gptr, num_graphs, doff, moff); count_launch();
   // large windows on the tensor-core path: thresholded candidate lists instead of dense N^2 blocks (MPN_KNN_DENSE=1: old path)
-  static const bool force_dense = getenv("MPN_KNN_DENSE") != nullptr;
+  const bool force_dense = getenv("MPN_KNN_DENSE") != nullptr;          // read per call: tests toggle it
   const bool tg = tc && max_n <= SEL_MAX_N && !force_dense && gram_thresholded_applies(h_gptr, num_graphs, top_k);
   int64_t scratch_rows = 0;
   if (tg) {

@@ -172,7 +172,7 @@ constexpr int G2_SMEM_BYTES = G2_SM_TMEM + 16;
 //   MODE 2  main pass over the UPPER-TRIANGULAR tiles: an entry (i, j) with d^2 <= tau_i is appended to row i's candidate
 //           list, with d^2 <= tau_j to row j's (one value serves both rows, so both see the same bits).
 // cand_select_kernel then ranks a row's ~100-300 candidates exactly like the dense row select would.
-constexpr int SAMPLE_COLS = 2 * TS, CAND_CAP = 512, TG_MIN_TILES = 8;
+constexpr int SAMPLE_COLS = 2 * TS, CAND_CAP = 512, TG_MIN_TILES = 8, TG_DEFAULT_MAX_K = 64;
 
 struct Gram2Args {
   const int64_t* frame; const int64_t* gptr; const int64_t* doff; const int64_t* tile_off; const int64_t* tri_off;
@@ -640,7 +640,11 @@ int gram_dist_blocks(const float* reid, int64_t dim, const int64_t* frame, const
 bool gram_thresholded_applies(const int64_t* h_gptr, int64_t num_graphs, int64_t top_k) {
   for (int64_t g = 0; g < num_graphs; ++g)
     if (h_gptr[g + 1] - h_gptr[g] < (int64_t)gram::TG_MIN_TILES * gram::TS) return false;
-  return top_k >= 1 && top_k <= gram::CAND_CAP / 4;
+  // The candidate lists grow with k: measured on 4 windows x 4,500 nodes (profiles/r02_config5_sweep.md) the thresholded build
+  // wins up to k = 50 (3.35 vs 4.17 ms per step at k = 25) and loses from k = 75 on (6.80 vs 5.50 ms), so the default gate is
+  // TG_DEFAULT_MAX_K; MPN_KNN_THRESHOLDED=1 extends it to the structural limit CAND_CAP / 4 (tests, measurements).
+  const bool force = getenv("MPN_KNN_THRESHOLDED") != nullptr;        // read per call: tests toggle it
+  return top_k >= 1 && top_k <= (force ? gram::CAND_CAP / 4 : gram::TG_DEFAULT_MAX_K);
 }
 
 int gram_thresholded_select(const float* reid, int64_t dim, const int64_t* frame, const int64_t* gptr, const int64_t* h_gptr,

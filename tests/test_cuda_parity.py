@@ -997,6 +997,33 @@ def test_config5_dense_crowd_window_matches_reference_golden(engine):
                                rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize('k', [25, 50, 100, 128])
+def test_thresholded_and_dense_knn_builds_keep_the_same_pairs(k, monkeypatch):
+    """The two tensor-core graph builds (thresholded candidate lists: default up to k = 64, forced up to k = 128 with
+    MPN_KNN_THRESHOLDED; dense blocks + fused row select: MPN_KNN_DENSE) and the exact fp32 build return identical pairs on
+    the configs[4] window (N = 4,500) next to a configs[1]-sized one."""
+    from mpntrackseg_b200.data.mot_graph import build_window_graphs
+    c = load_big_case('config5')
+    win = c['win']
+    ds = dict(c['ds'], top_k_nns=k)
+    tab = {kk: torch.from_numpy(v) for kk, v in synth.det_columns(win).items()}
+    tab.update(reid=win.reid, x=win.x.to(dev()))
+    w2 = synth.make_window(T=15, D=150, k=k, seed=11, node_feats='pooled', node_dim=win.x.shape[1], min_gap=2e-6)
+    tab2 = {kk: torch.from_numpy(v) for kk, v in synth.det_columns(w2).items()}
+    tab2.update(reid=w2.reid, x=w2.x.to(dev()))
+    got = {}
+    for name, env in (('thresholded', 'MPN_KNN_THRESHOLDED'), ('dense', 'MPN_KNN_DENSE')):
+        monkeypatch.setenv(env, '1')
+        got[name] = build_window_graphs([tab, tab2], ds, win.fps, device=dev(), engine='tc')
+        monkeypatch.delenv(env)
+    exact = build_window_graphs([tab, tab2], ds, win.fps, device=dev(), engine='fp32')
+    for name, b in got.items():
+        assert b.pair_ptr == exact.pair_ptr, (name, k)
+        assert torch.equal(b.edge_index, exact.edge_index), (name, k)
+        np.testing.assert_allclose(b.edge_attr.cpu().numpy(), exact.edge_attr.cpu().numpy(), rtol=3e-6, atol=1e-6)
+    assert torch.equal(got['thresholded'].edge_attr, got['dense'].edge_attr), k
+
+
 @pytest.mark.parametrize('engine', ENGINES)
 def test_window_beyond_5120_nodes_takes_the_general_select_path(engine):
     """A window of 5,400 detections is above the fused row-select limit (5,120): batch_row_kth_kernel / knn_pairs_kernel
