@@ -26,6 +26,10 @@ def _req(t, dtype, name):
         raise RuntimeError(f'{name}: must be a CUDA tensor (no CPU fallback)')
     if t.dtype != dtype:
         raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream (stream_ptr()); a tensor of another GPU would be dereferenced there
+        raise RuntimeError(f'{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}; '
+                           f'call under torch.cuda.device({t.device.index})')
     return t if t.is_contiguous() else t.contiguous()
 
 

@@ -17,6 +17,8 @@ CPU), the algorithms of
   sequence, per-edge averaging, undirected merge, pruning at 0.5; ``tracker_ref.py``)
 * ``src/mot_neural_solver/data/mot_graph.py:223-262``      (edge labels of the network-flow formulation)
 * ``src/mot_neural_solver/pl_module/pl_module.py:88-120``  (weighted BCE loss)
+* ``src/mot_neural_solver/utils/evaluation.py:370-414``, ``tracker/projectors.py:11-67``,
+  ``tracker/mpn_tracker.py:231-248``  (constraint statistics, greedy rounding, identities; ``rounding_ref.py``, numpy)
 
 and of the third-party ``torch-scatter==2.0.4`` calls made on that path
 (``scatter_add`` = index-add with zero fill, ``scatter_softmax`` =
@@ -27,5 +29,7 @@ Parity pinning: the reference holds NO test, golden vector or fixture for this p
 reference itself: ``tests/golden/make_golden.py`` imports the unmodified reference
 modules from ``/root/reference/src`` (with a ``torch_scatter`` stand-in), runs them on
 seeded synthetic windows and commits the outputs as ``tests/golden/*.npz``;
-``tests/test_oracle_golden.py`` checks this oracle against those files.
+``tests/test_oracle_golden.py`` checks this oracle against those files (model cases, the
+configs[4] window with 4,500 nodes, a 5,400-node window, tracker window + sequence, edge labels,
+rounding + identities).
 """

@@ -167,3 +167,72 @@ def test_loss_zero_positives_and_weighting():
     x = logits[0].view(-1)
     manual = (2.0 * lab * torch.nn.functional.softplus(-x) + (1 - lab) * torch.nn.functional.softplus(x)).mean()
     assert torch.allclose(l, manual, atol=1e-6)
+
+
+# ------------------------------------------------------------------ the large fixtures (BASELINE.json configs[4], > 5,120 nodes)
+def test_config5_graph_and_forward_match_reference():
+    """configs[4] (15 x 300 detections, k = 100; N = 4,500, E = 179 k): the oracle's edge list, features and logits against
+    the reference's own (tests/golden/config5.npz keeps a strided feature sample, two logit rows and the step means)."""
+    from cases import load_big_case
+    c = load_big_case('config5')
+    win, ds, gold = c['win'], c['ds'], c['gold']
+    g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds, inference_mode=False, max_frame_dist='max')
+    assert graph_ref.time_valid_pairs(win.frame, 'max').shape[1] == int(gold['n_candidates'])
+    assert np.array_equal(g['edge_index'].numpy(), gold['edge_index'].astype(np.int64))
+    assert np.array_equal(g['edge_attr'][::16].numpy(), gold['edge_attr_sample'])
+    with torch.no_grad():
+        out = mpn_ref.mpn_forward(c['P'], c['mp'], win.x, g['edge_index'], g['edge_attr'])
+    logits = torch.stack([t.view(-1) for t in out['classified_edges']])
+    # node state ~5e4 after 12 sum aggregations: fp32 summation-order noise is ~1e-4 relative on these logits
+    for row, key in ((-1, 'logits_last'), (0, 'logits_first')):
+        ref = gold[key]
+        assert np.all(np.abs(logits[row].numpy() - ref) <= 1e-3 * np.maximum(1.0, np.abs(ref)))
+    np.testing.assert_allclose(logits.double().mean(dim=1).numpy(), gold['logits_step_means'], rtol=1e-4, atol=1e-4)
+
+
+def test_big_window_pairs_match_reference():
+    """A 5,400-node window (tests/golden/big_window.npz): kept pairs and a sample of their distances."""
+    from cases import load_big_case
+    c = load_big_case('big_window')
+    win, ds, gold = c['win'], c['ds'], c['gold']
+    g = graph_ref.build_graph(win.frame, win.reid, synth.det_columns(win), win.fps, ds, inference_mode=False, max_frame_dist='max')
+    p = g['edge_index'].shape[1] // 2
+    assert np.array_equal(g['edge_index'][:, :p].numpy(), gold['pairs'].astype(np.int64))
+    assert np.array_equal(g['edge_attr'][:p:8, 5].numpy(), gold['reid_dist_sample'])
+
+
+# ------------------------------------------------------------------ rounding + identities (SURVEY.md f2)
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_rounding_oracle_matches_reference(tag):
+    """oracle/rounding_ref.py against the reference's compute_constr_satisfaction_rate / GreedyProjector and scipy's
+    connected_components (tests/golden/rounding.npz): integer work, bit-exact."""
+    from oracle import rounding_ref
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rounding.npz')))
+    n = int(gold[f'n_{tag}'])
+    ei, preds = gold[f'edge_index_{tag}'].astype(np.int64), gold[f'preds_{tag}']
+    r0 = (preds > 0.5).astype(np.float32)
+    both = np.concatenate((ei, ei[::-1]), axis=1)
+    rate_u, fin, fout = rounding_ref.constr_satisfaction_rate(both, n, np.concatenate((r0, r0)), undirected_edges=True)
+    assert rate_u == float(gold[f'rate_undirected_{tag}'])
+    assert np.array_equal(fin, gold[f'flow_in_{tag}']) and np.array_equal(fout, gold[f'flow_out_{tag}'])
+    rounded, rate = rounding_ref.greedy_project(ei, preds, n)
+    assert rate == float(gold[f'rate_{tag}'])
+    assert np.array_equal(rounded, gold[f'round_{tag}'])
+    assert int((rounded > r0).sum()) == 0                                    # the projection only switches edges off
+    ncomp, labels = rounding_ref.connected_components(ei, rounded, n)
+    assert ncomp == int(gold[f'ncomp_{tag}']) and np.array_equal(labels, gold[f'labels_{tag}'])
+
+
+def test_rounding_oracle_components_equal_scipy_on_random_graphs():
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    from oracle import rounding_ref
+    rng = np.random.default_rng(5)
+    for n, e in ((1, 0), (7, 3), (60, 45), (300, 500)):
+        ei = rng.integers(0, n, size=(2, e))
+        on = (rng.random(e) < 0.6).astype(np.float32)
+        ncomp, labels = rounding_ref.connected_components(ei, on, n)
+        m = on == 1
+        ref_n, ref_l = connected_components(csr_matrix((np.ones(int(m.sum()), dtype=int), tuple(ei[:, m])), shape=(n, n)),
+                                            directed=False, return_labels=True)
+        assert ncomp == ref_n and np.array_equal(labels, ref_l)
