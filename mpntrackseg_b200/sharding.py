@@ -31,3 +31,15 @@ def reduce_step_stats(elapsed_ms, counters, device=None, group=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
     return float(t[0]), c.tolist()
+
+
+def all_reduce_sum_(bucket, group=None):
+    """Sums the flat gradient ``bucket`` over the ranks IN PLACE (one collective: NCCL on GPUs, gloo on CPU) and returns
+    the world size, so the caller can take the mean inside its optimizer kernel (``grad_scale = 1 / world``).  Without an
+    initialised process group, or alone in it, nothing happens and 1 is returned.  This is the only exchange step of the
+    path: data-parallel training, pl_module.py:137-141 / scripts/train.py:76 spread over ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+    return 1

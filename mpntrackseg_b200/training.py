@@ -336,11 +336,8 @@ class CoreTrainer:
     # ---------------------------------------------------------------- optimizer
     def all_reduce_grads(self, group=None):
         """One summed all-reduce of the single flat gradient bucket (1.19 MB); NCCL on GPUs."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
-            return dist.get_world_size(group)
-        return 1
+        from .sharding import all_reduce_sum_
+        return all_reduce_sum_(self.grad, group)
 
     @property
     def t(self):

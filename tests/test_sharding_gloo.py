@@ -1,11 +1,12 @@
-"""World-size-2 gloo test (CPU) of the multi-GPU host logic: window sharding and step-stat reduction."""
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: window sharding, step-stat reduction, and the one
+exchange step of the path (the summed all-reduce of the flat gradient bucket in data-parallel training)."""
 import os
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mpntrackseg_b200.sharding import reduce_step_stats, shard_range
+from mpntrackseg_b200.sharding import all_reduce_sum_, reduce_step_stats, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -51,3 +52,44 @@ def test_two_rank_gloo_reduce_and_shards():
 
 def test_reduce_without_process_group_is_identity():
     assert reduce_step_stats(3.5, [1, 2]) == (3.5, [1.0, 2.0])
+
+
+def _bucket(rank, n=297_242):
+    """A rank's flat fp32 gradient bucket (the core network's 297 k parameters = 1.19 MB), seeded by the rank."""
+    return torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = _bucket(rank)
+    w = all_reduce_sum_(g)
+    out.put((rank, w, g.double().sum().item(), g[:4096].clone().numpy(), g[-7:].clone().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_bucket_all_reduce_equals_the_single_process_sum():
+    """Every rank ends up with the SAME bucket = the sum of the ranks' buckets (bit-equal to a local fp32 add for two
+    ranks), and gets the world size back for the mean the optimizer kernel takes."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _bucket(0) + _bucket(1)
+    for rank, w, total, head, tail in res:
+        assert w == 2
+        assert total == want.double().sum().item()
+        assert (head == want[:4096].numpy()).all() and (tail == want[-7:].numpy()).all()
+
+
+def test_gradient_all_reduce_without_process_group_is_identity():
+    g = _bucket(3, n=1000)
+    before = g.clone()
+    assert all_reduce_sum_(g) == 1 and torch.equal(g, before)
